@@ -1,0 +1,1343 @@
+// citam_b200.cu — B200 (sm_100a) implementation of CITAM's per-timestep loop.
+//
+// What it replaces in the reference (paths relative to the upstream repo):
+//   Agent.step + Schedule.get_next_position   citam/engine/core/agent.py:67-109,
+//                                             citam/engine/schedulers/office_schedule.py:632-638
+//   Floorplan.identify_this_location          citam/engine/map/floorplan.py:215-241 (+ space.py, geometry.py)
+//   CloseContactsCalculator.run               citam/engine/calculators/close_contacts_calculator.py:64-231
+//   ContactEvents.add_contact / statistics    citam/engine/calculators/contacts.py:92-294
+//
+// Pipeline per chunk of S time steps (all steps of a chunk are processed by one
+// launch each; accumulators are commutative so steps are independent):
+//   k_expand_bin  itinerary segments -> per-step SoA state rows (x, y, floor|loc) and the
+//                 uniform-grid histogram (one atomic per located agent returns its rank)
+//   k_scan        per-step exclusive scan of the cell histogram, staged in shared memory
+//   k_scatter     counting-sort scatter into cell order (16-byte records)
+//   k_pairs       half-neighbourhood pair test (own cell tail + right cell + 3 cells of the
+//                 row above) with the reference's float64 predicate, then accumulation into
+//                 the per-pair hash table, per-agent counters, per-coordinate histogram and
+//                 the optional contact log
+// All of this is HBM/L2-bound integer work; there is no GEMM in the path.
+
+#include "../../include/citam_b200.h"
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+// --------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(CITAM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+// --------------------------------------------------------------------------
+// device-side data
+// --------------------------------------------------------------------------
+struct FloorDev {
+  int32_t minx, miny, W, H;  // lattice of the location table
+  int32_t ncx, ncy;          // uniform grid over the same lattice
+  int32_t cell_base;         // first cell id of this floor
+  int32_t n_spaces;
+  const int16_t* lut;   // [H][W] space index, -1 = none; NULL = floor not loaded
+  const uint32_t* adj;  // n_spaces*n_spaces bits, NULL = no hallway graph
+};
+
+struct __align__(16) PairEntry {
+  unsigned long long key;  // (a1 << 32) | a2 with a1 < a2, 0 = empty
+  uint32_t dur;            // contact-steps
+  uint32_t nev;            // events (contact at t and not at t-1)
+  uint32_t first_inv;      // 0xFFFFFFFF - first contact step (max-reduced; 0 = none)
+  uint32_t pad0;
+  unsigned long long pad1;
+};
+static_assert(sizeof(PairEntry) == 32, "one 32-byte sector per pair entry");
+
+struct __align__(16) CoordEntry {
+  unsigned long long key;  // bit63 | floor<<56 | (sx+2^27)<<28 | (sy+2^27); 0 = empty
+  unsigned long long count;
+};
+
+struct DevCounters {
+  unsigned long long pair_tests;
+  unsigned long long contact_steps;
+  unsigned long long pair_used;
+  unsigned long long coord_used;
+  unsigned long long log_count;
+  unsigned long long overflow;
+  unsigned long long export_cursor;
+  unsigned long long stats[6];
+};
+
+struct Params {
+  int32_t N, F;
+  int32_t cell;
+  int32_t total_cells;
+  int32_t cells_stride;  // uint32 per step row of the histogram (>= total_cells+1, multiple of 4)
+  double D;
+  const FloorDev* floors;
+  const int4* segs;  // {t0 | floor<<24, x0, y0, dx&0xffff | dy<<16}
+  const long long* seg_off;
+  int32_t* rec_x;  // [(S+1)][N]  row 0 = halo step t_begin-1
+  int32_t* rec_y;
+  int32_t* rec_fl;  // floor<<16 | (loc & 0xffff); floor -1 = not in the facility
+  uint32_t* rank;   // [S][N]
+  uint32_t* cells;  // [S][cells_stride]
+  int4* sorted;     // [S][N] {x, y, agent, floor<<16|loc}
+  PairEntry* pairs;
+  unsigned long long pair_mask;
+  CoordEntry* coords;
+  unsigned long long coord_mask;
+  citam_contact* log;
+  unsigned long long log_cap;
+  uint32_t* agent_dur;
+  DevCounters* ctr;
+};
+
+#define OVF_PAIR 1ULL
+#define OVF_COORD 2ULL
+#define OVF_LOG 4ULL
+#define OVF_GRID 8ULL
+
+__device__ __forceinline__ int32_t pack_fl(int floor, int loc) {
+  return (int32_t)(((uint32_t)floor << 16) | ((uint32_t)loc & 0xffffu));
+}
+__device__ __forceinline__ int fl_floor(int32_t fl) { return fl >> 16; }
+__device__ __forceinline__ int fl_loc(int32_t fl) { return (int)(int16_t)(fl & 0xffff); }
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+__device__ __forceinline__ int lut_lookup(const FloorDev& fd, int x, int y) {
+  if (fd.lut == nullptr) return -1;
+  int fx = x - fd.minx, fy = y - fd.miny;
+  if ((unsigned)fx >= (unsigned)fd.W || (unsigned)fy >= (unsigned)fd.H) return -1;
+  return (int)__ldg(fd.lut + (size_t)fy * fd.W + fx);
+}
+
+__device__ __forceinline__ int cell_of(const FloorDev& fd, int cell, int x, int y) {
+  int cx = (x - fd.minx) / cell, cy = (y - fd.miny) / cell;
+  return fd.cell_base + cy * fd.ncx + cx;
+}
+
+// --------------------------------------------------------------------------
+// K1a: itinerary expansion + grid histogram.
+// One thread walks one agent through kRowsPerThread consecutive steps: the segment cursor
+// advances monotonically, the location table is touched only when the position changes, and
+// every store is coalesced over the 32 agents of a warp.
+// --------------------------------------------------------------------------
+constexpr int kRowsPerThread = 16;
+
+__global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int rows, int do_bin) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.N) return;
+  int r0 = blockIdx.y * kRowsPerThread;
+  long long sb = p.seg_off[a], se = p.seg_off[a + 1];
+  int t = t_first + r0;
+  long long lo = sb, hi = se;  // first segment with t0 > t
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    int t0 = __ldg(&p.segs[mid].x) & 0xffffff;
+    if (t0 <= t) lo = mid + 1; else hi = mid;
+  }
+  long long c = lo - 1;
+  int4 s = make_int4(0, 0, 0, 0);
+  int next_t0 = INT_MAX;
+  if (c >= sb) s = __ldg(&p.segs[c]);
+  if (c + 1 < se) next_t0 = __ldg(&p.segs[c + 1].x) & 0xffffff;
+  int lastx = INT_MIN, lasty = INT_MIN, lastf = -1, loc = -1;
+#pragma unroll 1
+  for (int r = 0; r < kRowsPerThread; ++r) {
+    int row = r0 + r;
+    if (row >= rows) break;
+    t = t_first + row;
+    while (t >= next_t0) {
+      ++c;
+      s = __ldg(&p.segs[c]);
+      next_t0 = (c + 1 < se) ? (__ldg(&p.segs[c + 1].x) & 0xffffff) : INT_MAX;
+    }
+    size_t o = (size_t)row * p.N + a;
+    if (c < sb || t < 0) {
+      p.rec_x[o] = 0;
+      p.rec_y[o] = 0;
+      p.rec_fl[o] = pack_fl(-1, -1);
+      continue;
+    }
+    int dt = t - (s.x & 0xffffff);
+    int f = (s.x >> 24) & 0xff;
+    int x = s.y + (int)(int16_t)(s.w & 0xffff) * dt;
+    int y = s.z + (int)(int16_t)((uint32_t)s.w >> 16) * dt;
+    if (x != lastx || y != lasty || f != lastf) {
+      loc = (f < p.F) ? lut_lookup(p.floors[f], x, y) : -1;
+      lastx = x; lasty = y; lastf = f;
+    }
+    p.rec_x[o] = x;
+    p.rec_y[o] = y;
+    p.rec_fl[o] = pack_fl(f, loc);
+    if (do_bin && row >= 1 && loc >= 0) {
+      int key = cell_of(p.floors[f], p.cell, x, y);
+      uint32_t rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
+      p.rank[(size_t)(row - 1) * p.N + a] = rk;
+    }
+  }
+}
+
+// K1b: histogram from caller-supplied state rows (the Calculator.run entry).
+__global__ void k_bin_states(Params p, int rows) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = blockIdx.y + 1;
+  if (a >= p.N || row >= rows) return;
+  size_t o = (size_t)row * p.N + a;
+  int32_t fl = p.rec_fl[o];
+  int f = fl_floor(fl), loc = fl_loc(fl);
+  if (f < 0 || loc < 0) return;
+  int x = p.rec_x[o], y = p.rec_y[o];
+  bool ok = f < p.F;
+  if (ok) {
+    const FloorDev& fd = p.floors[f];
+    int fx = x - fd.minx, fy = y - fd.miny;
+    ok = fd.lut != nullptr && (unsigned)fx < (unsigned)fd.W && (unsigned)fy < (unsigned)fd.H;
+  }
+  if (!ok) {  // caller says "located" but the point is outside the floor's grid
+    atomicOr(&p.ctr->overflow, OVF_GRID);
+    p.rec_fl[o] = pack_fl(f, -1);
+    return;
+  }
+  int key = cell_of(p.floors[f], p.cell, x, y);
+  uint32_t rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
+  p.rank[(size_t)(row - 1) * p.N + a] = rk;
+}
+
+__global__ void k_states_to_rec(const citam_agent_state* st, int N, int32_t* x, int32_t* y, int32_t* fl) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= N) return;
+  citam_agent_state s = st[a];
+  int f = s.floor < 0 ? -1 : s.floor;
+  int l = (f < 0 || s.loc < 0) ? -1 : s.loc;
+  x[a] = s.x; y[a] = s.y; fl[a] = pack_fl(f, l);
+}
+
+__global__ void k_rec_to_states(const int32_t* x, const int32_t* y, const int32_t* fl, int N, citam_agent_state* st) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= N) return;
+  citam_agent_state s;
+  s.x = x[a]; s.y = y[a]; s.floor = (int16_t)fl_floor(fl[a]); s.loc = (int16_t)fl_loc(fl[a]);
+  st[a] = s;
+}
+
+__global__ void k_fill_inactive(int32_t* x, int32_t* y, int32_t* fl, int N) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= N) return;
+  x[a] = 0; y[a] = 0; fl[a] = pack_fl(-1, -1);
+}
+
+// --------------------------------------------------------------------------
+// K2: per-step exclusive scan of the cell histogram (one CTA per step, in place).
+// cells[row][0..total_cells) counts -> starts; cells[row][total_cells] = located agents.
+// Warp shuffles scan 4 cells per thread; warp totals are combined through shared memory.
+// --------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads) k_scan(uint32_t* cells, int stride, int n /* total_cells+1 */) {
+  __shared__ uint32_t warp_off[32];
+  __shared__ uint32_t s_tot;
+  uint4* c4 = reinterpret_cast<uint4*>(cells + (size_t)blockIdx.x * stride);
+  const int n4 = (n + 3) >> 2;  // stride is a multiple of 4 and the padding is zero
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (int base = 0; base < n4; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < n4) v = c4[i];
+    uint32_t sum = v.x + v.y + v.z + v.w;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_off[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t wt = warp_off[lane];
+      uint32_t winc = wt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += o;
+      }
+      warp_off[lane] = winc - wt;
+      if (lane == 31) s_tot = winc;
+    }
+    __syncthreads();
+    uint32_t ex = carry + warp_off[w] + (inc - sum);
+    if (i < n4) {
+      uint4 o;
+      o.x = ex;
+      o.y = ex + v.x;
+      o.z = o.y + v.y;
+      o.w = o.z + v.z;
+      c4[i] = o;
+    }
+    carry += s_tot;
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------
+// K3: counting-sort scatter into cell order.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = blockIdx.y;
+  if (a >= p.N || row >= rows) return;
+  size_t o = (size_t)(row + 1) * p.N + a;
+  int32_t fl = p.rec_fl[o];
+  int f = fl_floor(fl), loc = fl_loc(fl);
+  if (f < 0 || loc < 0) return;
+  int x = p.rec_x[o], y = p.rec_y[o];
+  int key = cell_of(p.floors[f], p.cell, x, y);
+  uint32_t dest = p.cells[(size_t)row * p.cells_stride + key] + p.rank[(size_t)row * p.N + a];
+  p.sorted[(size_t)row * p.N + dest] = make_int4(x, y, a, fl);
+}
+
+// --------------------------------------------------------------------------
+// K4: pair test + accumulation.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ bool loc_rule(const FloorDev& fd, int l1, int l2) {
+  // close_contacts_calculator.py:111-124,173-203: same space, or both hallways with a graph edge
+  if (l1 == l2) return true;
+  if (fd.adj == nullptr) return false;
+  unsigned bit = (unsigned)l1 * (unsigned)fd.n_spaces + (unsigned)l2;
+  return (__ldg(fd.adj + (bit >> 5)) >> (bit & 31)) & 1u;
+}
+
+// has_edge(space_of_lower_id, space_of_higher_id): argument order as in the reference, which
+// matters only if a directed hallway graph is ever supplied
+__device__ __forceinline__ bool loc_rule_ordered(const FloorDev& fd, int ida, int la, int idb, int lb) {
+  return ida < idb ? loc_rule(fd, la, lb) : loc_rule(fd, lb, la);
+}
+
+__device__ __forceinline__ bool within(int dx, int dy, double D) {
+  // scipy pdist (euclidean) on integer coordinates: sqrt(dx*dx+dy*dy) in float64, then the
+  // strict `< contact_distance` of np.argwhere (close_contacts_calculator.py:169-171).
+  // dx, dy are exact integers, so the squared sum is exact and one IEEE sqrt reproduces it.
+  long long s = (long long)dx * dx + (long long)dy * dy;
+  return __dsqrt_rn((double)s) < D;
+}
+
+__device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32_t a2, uint32_t t,
+                                            uint32_t add_dur, uint32_t add_nev) {
+  unsigned long long key = ((unsigned long long)a1 << 32) | a2;
+  unsigned long long h = mix64(key) & p.pair_mask;
+  bool found = false;
+  for (unsigned long long probe = 0; probe <= p.pair_mask; ++probe) {
+    unsigned long long k = *(volatile unsigned long long*)&p.pairs[h].key;
+    if (k == key) { found = true; break; }
+    if (k == 0ULL) {
+      unsigned long long old = atomicCAS(&p.pairs[h].key, 0ULL, key);
+      if (old == 0ULL) { atomicAdd(&p.ctr->pair_used, 1ULL); found = true; break; }
+      if (old == key) { found = true; break; }
+    }
+    h = (h + 1) & p.pair_mask;
+  }
+  if (!found) { atomicOr(&p.ctr->overflow, OVF_PAIR); return; }
+  atomicAdd(&p.pairs[h].dur, add_dur);
+  if (add_nev) atomicAdd(&p.pairs[h].nev, add_nev);
+  // min over every contact step seen by this engine, so partial ranges / merged shards agree
+  atomicMax(&p.pairs[h].first_inv, 0xFFFFFFFFu - t);
+}
+
+__device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx, int sy, unsigned long long add) {
+  unsigned long long key = (1ULL << 63) | ((unsigned long long)(floor & 0x7f) << 56) |
+                           ((unsigned long long)((uint32_t)(sx + (1 << 27)) & 0xfffffffu) << 28) |
+                           (unsigned long long)((uint32_t)(sy + (1 << 27)) & 0xfffffffu);
+  unsigned long long h = mix64(key) & p.coord_mask;
+  bool found = false;
+  for (unsigned long long probe = 0; probe <= p.coord_mask; ++probe) {
+    unsigned long long k = *(volatile unsigned long long*)&p.coords[h].key;
+    if (k == key) { found = true; break; }
+    if (k == 0ULL) {
+      unsigned long long old = atomicCAS(&p.coords[h].key, 0ULL, key);
+      if (old == 0ULL) { atomicAdd(&p.ctr->coord_used, 1ULL); found = true; break; }
+      if (old == key) { found = true; break; }
+    }
+    h = (h + 1) & p.coord_mask;
+  }
+  if (!found) { atomicOr(&p.ctr->overflow, OVF_COORD); return; }
+  atomicAdd(&p.coords[h].count, add);
+}
+
+// Was the pair in contact at the previous step?  Full predicate on the halo/previous row
+// (contacts.py:131-133: an event continues iff last.start_step + last.duration == step).
+__device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
+  int32_t f1 = p.rec_fl[prow_off + a1], f2 = p.rec_fl[prow_off + a2];
+  int fl1 = fl_floor(f1), fl2 = fl_floor(f2);
+  int l1 = fl_loc(f1), l2 = fl_loc(f2);
+  if (fl1 < 0 || fl1 != fl2 || l1 < 0 || l2 < 0) return false;
+  int x1 = p.rec_x[prow_off + a1], x2 = p.rec_x[prow_off + a2];
+  int y1 = p.rec_y[prow_off + a1], y2 = p.rec_y[prow_off + a2];
+  long long dx = (long long)x2 - x1, dy = (long long)y2 - y1;
+  long long lim = (long long)p.D + 1;
+  if (dx > lim || dx < -lim || dy > lim || dy < -lim) return false;
+  if (!within((int)dx, (int)dy, p.D)) return false;
+  return loc_rule(p.floors[fl1], l1, l2);
+}
+
+__device__ __forceinline__ void on_contact(const Params& p, int row, uint32_t t, const int4& me, const int4& ot) {
+  uint32_t a1 = (uint32_t)min(me.z, ot.z), a2 = (uint32_t)max(me.z, ot.z);
+  bool was = contact_prev(p, (size_t)row * p.N, a1, a2);  // rec row `row` holds step t-1
+  pair_upsert(p, a1, a2, t, 1u, was ? 0u : 1u);
+  atomicAdd(&p.agent_dur[a1], 1u);
+  atomicAdd(&p.agent_dur[a2], 1u);
+  coord_upsert(p, fl_floor(me.w), me.x + ot.x, me.y + ot.y, 1ULL);
+  if (p.log_cap) {
+    // warp-aggregated append: one atomic per converged group of lanes
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&p.ctr->log_count, (unsigned long long)g.size());
+    base = g.shfl(base, 0) + g.thread_rank();
+    if (base < p.log_cap) {
+      citam_contact c; c.step = t; c.a1 = a1; c.a2 = a2;
+      p.log[base] = c;
+    } else {
+      atomicOr(&p.ctr->overflow, OVF_LOG);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pairs(Params p, int t_begin, int rows /* S */) {
+  int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+  int row = blockIdx.y;
+  unsigned long long tests = 0, hits = 0;
+  const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
+  int total = (int)cs[p.total_cells];
+  if (q0 < total) {
+    const int4* srt = p.sorted + (size_t)row * p.N;
+    int4 me = srt[q0];
+    int f = fl_floor(me.w), loc = fl_loc(me.w);
+    const FloorDev fd = p.floors[f];
+    int cx = (me.x - fd.minx) / p.cell, cy = (me.y - fd.miny) / p.cell;
+    int rowbase = fd.cell_base + cy * fd.ncx;
+    uint32_t t = (uint32_t)(t_begin + row);
+    // own row: rest of my cell + the cell to the right
+    int end = (int)cs[rowbase + min(cx + 1, fd.ncx - 1) + 1];
+    for (int q = q0 + 1; q < end; ++q) {
+      int4 ot = srt[q];
+      ++tests;
+      if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
+        ++hits;
+        on_contact(p, row, t, me, ot);
+      }
+    }
+    // row above: three cells
+    if (cy + 1 < fd.ncy) {
+      int rb2 = rowbase + fd.ncx;
+      int qb = (int)cs[rb2 + max(cx - 1, 0)];
+      int qe = (int)cs[rb2 + min(cx + 1, fd.ncx - 1) + 1];
+      for (int q = qb; q < qe; ++q) {
+        int4 ot = srt[q];
+        ++tests;
+        if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
+          ++hits;
+          on_contact(p, row, t, me, ot);
+        }
+      }
+    }
+  }
+  // one counter update per warp
+  for (int d = 16; d > 0; d >>= 1) {
+    tests += __shfl_down_sync(0xffffffffu, tests, d);
+    hits += __shfl_down_sync(0xffffffffu, hits, d);
+  }
+  if ((threadIdx.x & 31) == 0 && (tests | hits)) {
+    atomicAdd(&p.ctr->pair_tests, tests);
+    if (hits) atomicAdd(&p.ctr->contact_steps, hits);
+  }
+}
+
+// --------------------------------------------------------------------------
+// K0: location table.  One thread per lattice point evaluates the reference's rule
+// (floorplan.py:215-241 first match; space.py:194-280; geometry.py:31-127,558-588) in
+// float64 with explicitly rounded operations (no FMA contraction).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ bool in_box(double px, double py, double qx, double qy, double rx, double ry) {
+  return qx <= fmax(px, rx) && qx >= fmin(px, rx) && qy <= fmax(py, ry) && qy >= fmin(py, ry);
+}
+
+__device__ __forceinline__ int orient(double px, double py, double qx, double qy, double rx, double ry) {
+  double v = __dsub_rn(__dmul_rn(__dsub_rn(qy, py), __dsub_rn(rx, qx)),
+                       __dmul_rn(__dsub_rn(qx, px), __dsub_rn(ry, qy)));
+  return v == 0.0 ? 0 : (v > 0.0 ? 1 : 2);
+}
+
+__device__ bool segments_cross(double p1x, double p1y, double q1x, double q1y, double p2x, double p2y,
+                               double q2x, double q2y) {
+  int o1 = orient(p1x, p1y, q1x, q1y, p2x, p2y);
+  int o2 = orient(p1x, p1y, q1x, q1y, q2x, q2y);
+  int o3 = orient(p2x, p2y, q2x, q2y, p1x, p1y);
+  int o4 = orient(p2x, p2y, q2x, q2y, q1x, q1y);
+  if (o1 != o2 && o3 != o4) return true;
+  if (o1 == 0 && in_box(p1x, p1y, p2x, p2y, q1x, q1y)) return true;
+  if (o2 == 0 && in_box(p1x, p1y, q2x, q2y, q1x, q1y)) return true;
+  if (o3 == 0 && in_box(p2x, p2y, p1x, p1y, q2x, q2y)) return true;
+  if (o4 == 0 && in_box(p2x, p2y, q1x, q1y, q2x, q2y)) return true;
+  return false;
+}
+
+__global__ void __launch_bounds__(128) k_build_lut(int minx, int miny, int W, int H, int n_spaces,
+                                                   const citam_space* __restrict__ spaces,
+                                                   const citam_boundary* __restrict__ bnd,
+                                                   const citam_door* __restrict__ doors, int16_t* __restrict__ lut) {
+  int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  int iy = blockIdx.y;
+  if (ix >= W || iy >= H) return;
+  int xi = minx + ix, yi = miny + iy;
+  double x = (double)xi, y = (double)yi;
+  const double INF = 1e10;
+  int result = -1;
+  for (int s = 0; s < n_spaces && result < 0; ++s) {
+    citam_space sp = spaces[s];
+    if (xi < sp.bb_xmin || xi > sp.bb_xmax || yi < sp.bb_ymin || yi > sp.bb_ymax) continue;
+    bool inside = false;
+    for (int d = sp.door_begin; d < sp.door_end && !inside; ++d) {
+      citam_door dr = doors[d];
+      inside = in_box(dr.sx, dr.sy, x, y, dr.ex, dr.ey);
+    }
+    for (int b = sp.seg_begin; b < sp.seg_end && !inside; ++b) {
+      citam_boundary sg = bnd[b];
+      if (!sg.long_enough) continue;
+      if ((x == sg.sx && y == sg.sy) || (x == sg.ex && y == sg.ey)) { inside = true; break; }
+      if (in_box(sg.sx, sg.sy, x, y, sg.ex, sg.ey)) {
+        double ddx = __dsub_rn(x, sg.sx), ddy = __dsub_rn(y, sg.sy);
+        double h = hypot(ddx, ddy);
+        // normal of start->point: -1j * (d / |d|)  ==  (d.imag/|d|, -d.real/|d|)
+        double n2x = __ddiv_rn(ddy, h), n2y = -__ddiv_rn(ddx, h);
+        if (fabs(__dsub_rn(sg.nx, n2x)) < 1e-3 && fabs(__dsub_rn(sg.ny, n2y)) < 1e-3) inside = true;
+      }
+    }
+    if (!inside) {
+      double ex[8] = {INF, __dsub_rn(x, 5.0), -INF, __dsub_rn(x, 5.0), INF, INF, -INF, -INF};
+      double ey[8] = {__dadd_rn(y, 5.0), INF, __dadd_rn(y, 5.0), -INF, INF, -INF, INF, -INF};
+#pragma unroll 1
+      for (int r = 0; r < 8 && !inside; ++r) {
+        int count = 0;
+        for (int b = sp.seg_begin; b < sp.seg_end; ++b) {
+          citam_boundary sg = bnd[b];
+          count += segments_cross(sg.sx, sg.sy, sg.ex, sg.ey, x, y, ex[r], ey[r]) ? 1 : 0;
+        }
+        inside = (count & 1) != 0;
+      }
+    }
+    if (inside) result = s;
+  }
+  lut[(size_t)iy * W + ix] = (int16_t)result;
+}
+
+// --------------------------------------------------------------------------
+// K5: finalize — compaction of the tables and the integer sums of the statistics.
+// --------------------------------------------------------------------------
+__global__ void k_compact_pairs(const PairEntry* tab, unsigned long long cap, citam_pair* out,
+                                unsigned long long out_cap, DevCounters* ctr) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  PairEntry e = tab[i];
+  if (e.key == 0ULL) return;
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
+  base = g.shfl(base, 0) + g.thread_rank();
+  if (base >= out_cap) return;
+  citam_pair r;
+  r.a1 = (uint32_t)(e.key >> 32);
+  r.a2 = (uint32_t)(e.key & 0xffffffffu);
+  r.first_step = 0xFFFFFFFFu - e.first_inv;
+  r.n_events = e.nev;
+  r.duration = e.dur;
+  out[base] = r;
+}
+
+__global__ void k_compact_coords(const CoordEntry* tab, unsigned long long cap, citam_coord* out,
+                                 unsigned long long out_cap, DevCounters* ctr) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  CoordEntry e = tab[i];
+  if (e.key == 0ULL) return;
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
+  base = g.shfl(base, 0) + g.thread_rank();
+  if (base >= out_cap) return;
+  citam_coord r;
+  r.floor = (int32_t)((e.key >> 56) & 0x7f);
+  r.sx = (int32_t)((e.key >> 28) & 0xfffffffu) - (1 << 27);
+  r.sy = (int32_t)(e.key & 0xfffffffu) - (1 << 27);
+  r.reserved = 0;
+  r.count = e.count;
+  out[base] = r;
+}
+
+// pass 1: per-agent event sums and "has a pair" flags; pass 2: reduce over agents
+__global__ void k_stats_pairs(const PairEntry* tab, unsigned long long cap, uint32_t* agent_nev,
+                              uint32_t* agent_has, DevCounters* ctr) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long dur = 0, np = 0;
+  if (i < cap) {
+    PairEntry e = tab[i];
+    if (e.key != 0ULL) {
+      uint32_t a1 = (uint32_t)(e.key >> 32), a2 = (uint32_t)(e.key & 0xffffffffu);
+      atomicAdd(&agent_nev[a1], e.nev);
+      atomicAdd(&agent_nev[a2], e.nev);
+      agent_has[a1] = 1;
+      agent_has[a2] = 1;
+      dur = e.dur;
+      np = 1;
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    dur += __shfl_down_sync(0xffffffffu, dur, d);
+    np += __shfl_down_sync(0xffffffffu, np, d);
+  }
+  if ((threadIdx.x & 31) == 0 && np) {
+    atomicAdd(&ctr->stats[0], dur);
+    atomicAdd(&ctr->stats[1], np);
+  }
+}
+
+__global__ void k_stats_agents(const uint32_t* agent_nev, const uint32_t* agent_has, int N, DevCounters* ctr) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long has = 0, nev = 0, mx = 0;
+  if (a < N) { has = agent_has[a]; nev = agent_nev[a]; mx = nev; }
+  for (int d = 16; d > 0; d >>= 1) {
+    has += __shfl_down_sync(0xffffffffu, has, d);
+    nev += __shfl_down_sync(0xffffffffu, nev, d);
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+  }
+  if ((threadIdx.x & 31) == 0 && (has | nev)) {
+    atomicAdd(&ctr->stats[2], has);
+    atomicAdd(&ctr->stats[3], nev);
+    atomicMax(&ctr->stats[4], mx);
+  }
+}
+
+__global__ void k_merge_pairs(Params p, const citam_pair* in, unsigned long long n) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  citam_pair r = in[i];
+  pair_upsert(p, r.a1, r.a2, r.first_step, (uint32_t)r.duration, r.n_events);
+}
+
+__global__ void k_merge_coords(Params p, const citam_coord* in, unsigned long long n) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  citam_coord r = in[i];
+  coord_upsert(p, r.floor, r.sx, r.sy, r.count);
+}
+
+__global__ void k_repack_segments(const citam_segment* in, long long n, int4* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  citam_segment s = in[i];
+  out[i] = make_int4((s.t0 & 0xffffff) | ((int)(s.floor & 0xff) << 24), s.x0, s.y0,
+                     (int)(((uint32_t)(uint16_t)s.dx) | ((uint32_t)(uint16_t)s.dy << 16)));
+}
+
+// --------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------
+struct citam_engine {
+  citam_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int N = 0, F = 0, cell = 1;
+  double D = 6.0;
+  std::vector<FloorDev> floors_h;
+  std::vector<int16_t*> lut_d;
+  std::vector<uint32_t*> adj_d;
+  FloorDev* floors_d = nullptr;
+  bool floors_dirty = true;
+  int total_cells = 0, cells_stride = 4;
+
+  int4* segs_d = nullptr;
+  long long* seg_off_d = nullptr;
+  long long n_segs = 0;
+  bool have_itin = false;
+
+  int S = 0;  // chunk capacity in steps
+  int32_t *rec_x = nullptr, *rec_y = nullptr, *rec_fl = nullptr;
+  uint32_t* rank = nullptr;
+  uint32_t* cells = nullptr;
+  int4* sorted = nullptr;
+
+  PairEntry* pairs = nullptr;
+  unsigned long long pair_cap = 0;
+  CoordEntry* coords = nullptr;
+  unsigned long long coord_cap = 0;
+  citam_contact* log = nullptr;
+  unsigned long long log_cap = 0;
+  uint32_t* agent_dur = nullptr;
+  uint32_t *agent_nev = nullptr, *agent_has = nullptr;
+  DevCounters* ctr_d = nullptr;
+
+  // Calculator.run entry: previous explicit state row
+  int32_t *prev_x = nullptr, *prev_y = nullptr, *prev_fl = nullptr;
+  long long prev_step = LLONG_MIN;
+  citam_agent_state* states_d = nullptr;
+
+  unsigned long long agent_steps = 0, launches = 0;
+  bool timing = false;
+  struct Ev { cudaEvent_t a, b; int kind; };
+  std::vector<Ev> evs;
+  double t_ms[CITAM_N_KERNELS] = {0};
+  unsigned long long t_n[CITAM_N_KERNELS] = {0};
+};
+
+static unsigned long long next_pow2(unsigned long long v) {
+  unsigned long long p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct Timed {
+  citam_engine* e;
+  int kind;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timed(citam_engine* e_, int k) : e(e_), kind(k) {
+    e->launches++;
+    if (e->timing) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, e->stream);
+    }
+  }
+  ~Timed() {
+    if (e->timing) {
+      cudaEventRecord(b, e->stream);
+      e->evs.push_back({a, b, kind});
+    }
+  }
+};
+
+static void drain_timings(citam_engine* e) {
+  for (auto& v : e->evs) {
+    cudaEventSynchronize(v.b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, v.a, v.b);
+    e->t_ms[v.kind] += ms;
+    e->t_n[v.kind]++;
+    cudaEventDestroy(v.a);
+    cudaEventDestroy(v.b);
+  }
+  e->evs.clear();
+}
+
+static Params make_params(citam_engine* e) {
+  Params p{};
+  p.N = e->N; p.F = e->F; p.cell = e->cell; p.total_cells = e->total_cells; p.cells_stride = e->cells_stride;
+  p.D = e->D; p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
+  p.rec_x = e->rec_x; p.rec_y = e->rec_y; p.rec_fl = e->rec_fl; p.rank = e->rank; p.cells = e->cells;
+  p.sorted = e->sorted; p.pairs = e->pairs; p.pair_mask = e->pair_cap - 1; p.coords = e->coords;
+  p.coord_mask = e->coord_cap - 1; p.log = e->log; p.log_cap = e->log_cap; p.agent_dur = e->agent_dur;
+  p.ctr = e->ctr_d;
+  return p;
+}
+
+static void free_chunk(citam_engine* e) {
+  cudaFree(e->rec_x); cudaFree(e->rec_y); cudaFree(e->rec_fl); cudaFree(e->rank); cudaFree(e->cells);
+  cudaFree(e->sorted);
+  e->rec_x = e->rec_y = e->rec_fl = nullptr; e->rank = nullptr; e->cells = nullptr; e->sorted = nullptr;
+  e->S = 0;
+}
+
+// Upload floor descriptors and (re)size the chunk buffers for `want_steps` steps.
+static int ensure_ready(citam_engine* e, int want_steps) {
+  CK(cudaSetDevice(e->device));
+  if (e->floors_dirty) {
+    int base = 0;
+    for (auto& f : e->floors_h) {
+      f.ncx = f.lut ? (f.W + e->cell - 1) / e->cell : 0;
+      f.ncy = f.lut ? (f.H + e->cell - 1) / e->cell : 0;
+      f.cell_base = base;
+      base += f.ncx * f.ncy;
+    }
+    e->total_cells = base;
+    e->cells_stride = ((base + 1) + 3) & ~3;
+    CK(cudaMemcpyAsync(e->floors_d, e->floors_h.data(), sizeof(FloorDev) * e->F, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->floors_dirty = false;
+    free_chunk(e);
+  }
+  if (e->S >= want_steps && e->rec_x) return CITAM_OK;
+  free_chunk(e);
+  int S = want_steps;
+  size_t n = (size_t)e->N;
+  CK(cudaMalloc(&e->rec_x, sizeof(int32_t) * n * (S + 1)));
+  CK(cudaMalloc(&e->rec_y, sizeof(int32_t) * n * (S + 1)));
+  CK(cudaMalloc(&e->rec_fl, sizeof(int32_t) * n * (S + 1)));
+  CK(cudaMalloc(&e->rank, sizeof(uint32_t) * n * S));
+  CK(cudaMalloc(&e->cells, sizeof(uint32_t) * (size_t)e->cells_stride * S));
+  CK(cudaMalloc(&e->sorted, sizeof(int4) * n * S));
+  e->S = S;
+  return CITAM_OK;
+}
+
+static int pick_chunk(citam_engine* e, int steps) {
+  if (e->cfg.steps_per_chunk > 0) return std::min(steps, e->cfg.steps_per_chunk);
+  // ~8M agent-steps per launch group, bounded by 1 GiB of histogram rows
+  long long by_agents = std::max(1LL, (8LL << 20) / std::max(1, e->N));
+  long long by_cells = std::max(1LL, (1LL << 28) / std::max(4, e->cells_stride));
+  long long s = std::min(by_agents, by_cells);
+  s = std::min<long long>(s, 4096);
+  s = std::max<long long>(s, 1);
+  return (int)std::min<long long>(s, steps);
+}
+
+// bin (already done by caller) -> scan -> scatter -> pairs for `rows` steps starting at t_begin
+static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_SCAN);
+    k_scan<<<rows, kScanThreads, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1);
+  }
+  {
+    Timed tm(e, CITAM_K_SCATTER);
+    dim3 g((e->N + 255) / 256, rows);
+    k_scatter<<<g, 256, 0, e->stream>>>(p, rows);
+  }
+  {
+    Timed tm(e, CITAM_K_PAIRS);
+    dim3 g((e->N + 255) / 256, rows);
+    k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows);
+  }
+  CK(cudaGetLastError());
+  return CITAM_OK;
+}
+
+static int check_overflow(citam_engine* e) {
+  DevCounters c;
+  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (c.overflow & OVF_PAIR) return fail(CITAM_ERR_CAPACITY, "pair table full (%llu slots): raise pair_capacity", e->pair_cap);
+  if (c.overflow & OVF_COORD) return fail(CITAM_ERR_CAPACITY, "coordinate table full (%llu slots): raise coord_capacity", e->coord_cap);
+  if (c.overflow & OVF_LOG) return fail(CITAM_ERR_CAPACITY, "contact log full (%llu records): raise log_capacity", e->log_cap);
+  if (c.overflow & OVF_GRID) return fail(CITAM_ERR_INVALID, "an agent was given a location but lies outside its floor's lattice");
+  return CITAM_OK;
+}
+
+extern "C" {
+
+int citam_abi_version(void) { return CITAM_ABI_VERSION; }
+const char* citam_last_error(void) { return g_err.c_str(); }
+
+int citam_create(const citam_config* cfg, citam_engine** out) {
+  if (!cfg || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  if (cfg->n_agents <= 0 || cfg->n_floors <= 0 || cfg->n_floors > 127)
+    return fail(CITAM_ERR_INVALID, "n_agents must be > 0 and n_floors in 1..127");
+  if (!(cfg->contact_distance >= 0.0) || cfg->contact_distance > 1e6)
+    return fail(CITAM_ERR_INVALID, "contact_distance out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(CITAM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(CITAM_ERR_INVALID, "device %d out of range", cfg->device);
+  CK(cudaSetDevice(cfg->device));
+  citam_engine* e = new citam_engine();
+  e->cfg = *cfg;
+  e->device = cfg->device;
+  e->N = cfg->n_agents;
+  e->F = cfg->n_floors;
+  e->D = cfg->contact_distance;
+  int mincell = (int)std::ceil(cfg->contact_distance);
+  if (mincell < 1) mincell = 1;
+  e->cell = cfg->cell_size > 0 ? std::max(cfg->cell_size, mincell) : mincell;
+  e->timing = (cfg->flags & CITAM_FLAG_TIMING) != 0;
+  e->floors_h.assign(e->F, FloorDev{});
+  e->lut_d.assign(e->F, nullptr);
+  e->adj_d.assign(e->F, nullptr);
+  e->pair_cap = next_pow2(cfg->pair_capacity ? cfg->pair_capacity : std::max<unsigned long long>(1ULL << 16, 64ULL * e->N));
+  e->coord_cap = next_pow2(cfg->coord_capacity ? cfg->coord_capacity : std::max<unsigned long long>(1ULL << 16, 16ULL * e->N));
+  e->log_cap = cfg->log_capacity;
+  *out = e;
+  size_t n = (size_t)e->N;
+  CK(cudaMalloc(&e->floors_d, sizeof(FloorDev) * e->F));
+  CK(cudaMalloc(&e->pairs, sizeof(PairEntry) * e->pair_cap));
+  CK(cudaMalloc(&e->coords, sizeof(CoordEntry) * e->coord_cap));
+  if (e->log_cap) CK(cudaMalloc(&e->log, sizeof(citam_contact) * e->log_cap));
+  CK(cudaMalloc(&e->agent_dur, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->agent_nev, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->agent_has, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->ctr_d, sizeof(DevCounters)));
+  CK(cudaMalloc(&e->prev_x, sizeof(int32_t) * n));
+  CK(cudaMalloc(&e->prev_y, sizeof(int32_t) * n));
+  CK(cudaMalloc(&e->prev_fl, sizeof(int32_t) * n));
+  CK(cudaMalloc(&e->states_d, sizeof(citam_agent_state) * n));
+  return citam_reset(e);
+}
+
+void citam_destroy(citam_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  drain_timings(e);
+  free_chunk(e);
+  for (auto p : e->lut_d) cudaFree(p);
+  for (auto p : e->adj_d) cudaFree(p);
+  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->seg_off_d); cudaFree(e->pairs); cudaFree(e->coords);
+  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->ctr_d);
+  cudaFree(e->prev_x); cudaFree(e->prev_y); cudaFree(e->prev_fl); cudaFree(e->states_d);
+  delete e;
+}
+
+int citam_set_stream(citam_engine* e, void* s) {
+  if (!e) return fail(CITAM_ERR_INVALID, "null engine");
+  e->stream = (cudaStream_t)s;
+  return CITAM_OK;
+}
+
+int citam_reset(citam_engine* e) {
+  if (!e) return fail(CITAM_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->pairs, 0, sizeof(PairEntry) * e->pair_cap, e->stream));
+  CK(cudaMemsetAsync(e->coords, 0, sizeof(CoordEntry) * e->coord_cap, e->stream));
+  CK(cudaMemsetAsync(e->agent_dur, 0, sizeof(uint32_t) * (size_t)e->N, e->stream));
+  CK(cudaMemsetAsync(e->ctr_d, 0, sizeof(DevCounters), e->stream));
+  e->prev_step = LLONG_MIN;
+  e->agent_steps = 0;
+  return CITAM_OK;
+}
+
+static int install_lut(citam_engine* e, int floor, int minx, int miny, int W, int H, int n_spaces) {
+  if (floor < 0 || floor >= e->F) return fail(CITAM_ERR_INVALID, "floor %d out of range", floor);
+  if (W <= 0 || H <= 0 || (long long)W * H > (1LL << 31)) return fail(CITAM_ERR_INVALID, "bad lattice %dx%d", W, H);
+  if (n_spaces < 0 || n_spaces > 32767) return fail(CITAM_ERR_INVALID, "n_spaces must be <= 32767");
+  CK(cudaSetDevice(e->device));
+  cudaFree(e->lut_d[floor]);
+  e->lut_d[floor] = nullptr;
+  CK(cudaMalloc(&e->lut_d[floor], sizeof(int16_t) * (size_t)W * H));
+  FloorDev& f = e->floors_h[floor];
+  f.minx = minx; f.miny = miny; f.W = W; f.H = H; f.n_spaces = n_spaces; f.lut = e->lut_d[floor];
+  e->floors_dirty = true;
+  return CITAM_OK;
+}
+
+int citam_set_floor_lut(citam_engine* e, int32_t floor, int32_t minx, int32_t miny, int32_t W, int32_t H,
+                        int32_t n_spaces, const int16_t* lut) {
+  if (!e || !lut) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = install_lut(e, floor, minx, miny, W, H, n_spaces);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->lut_d[floor], lut, sizeof(int16_t) * (size_t)W * H, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return CITAM_OK;
+}
+
+int citam_build_floor_lut(citam_engine* e, int32_t floor, int32_t minx, int32_t miny, int32_t W, int32_t H,
+                          int32_t n_spaces, const citam_space* spaces, int32_t n_boundaries,
+                          const citam_boundary* boundaries, int32_t n_doors, const citam_door* doors) {
+  if (!e || (n_spaces > 0 && !spaces)) return fail(CITAM_ERR_INVALID, "null argument");
+  for (int s = 0; s < n_spaces; ++s) {
+    const citam_space& sp = spaces[s];
+    if (sp.seg_begin < 0 || sp.seg_end > n_boundaries || sp.seg_begin > sp.seg_end || sp.door_begin < 0 ||
+        sp.door_end > n_doors || sp.door_begin > sp.door_end)
+      return fail(CITAM_ERR_INVALID, "space %d has a bad segment/door range", s);
+  }
+  int rc = install_lut(e, floor, minx, miny, W, H, n_spaces);
+  if (rc) return rc;
+  citam_space* sp_d = nullptr;
+  citam_boundary* b_d = nullptr;
+  citam_door* d_d = nullptr;
+  CK(cudaMalloc(&sp_d, sizeof(citam_space) * std::max(1, n_spaces)));
+  CK(cudaMalloc(&b_d, sizeof(citam_boundary) * std::max(1, n_boundaries)));
+  CK(cudaMalloc(&d_d, sizeof(citam_door) * std::max(1, n_doors)));
+  if (n_spaces) CK(cudaMemcpyAsync(sp_d, spaces, sizeof(citam_space) * n_spaces, cudaMemcpyHostToDevice, e->stream));
+  if (n_boundaries) CK(cudaMemcpyAsync(b_d, boundaries, sizeof(citam_boundary) * n_boundaries, cudaMemcpyHostToDevice, e->stream));
+  if (n_doors) CK(cudaMemcpyAsync(d_d, doors, sizeof(citam_door) * n_doors, cudaMemcpyHostToDevice, e->stream));
+  {
+    Timed tm(e, CITAM_K_LUT);
+    dim3 g((W + 127) / 128, H);
+    k_build_lut<<<g, 128, 0, e->stream>>>(minx, miny, W, H, n_spaces, sp_d, b_d, d_d, e->lut_d[floor]);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(sp_d); cudaFree(b_d); cudaFree(d_d);
+  return CITAM_OK;
+}
+
+int citam_get_floor_lut(citam_engine* e, int32_t floor, int16_t* out) {
+  if (!e || !out || floor < 0 || floor >= e->F || !e->lut_d[floor]) return fail(CITAM_ERR_INVALID, "floor has no table");
+  CK(cudaSetDevice(e->device));
+  const FloorDev& f = e->floors_h[floor];
+  CK(cudaMemcpyAsync(out, e->lut_d[floor], sizeof(int16_t) * (size_t)f.W * f.H, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return CITAM_OK;
+}
+
+int citam_set_floor_adjacency(citam_engine* e, int32_t floor, int32_t n_spaces, const uint8_t* adj) {
+  if (!e || floor < 0 || floor >= e->F) return fail(CITAM_ERR_INVALID, "floor out of range");
+  CK(cudaSetDevice(e->device));
+  cudaFree(e->adj_d[floor]);
+  e->adj_d[floor] = nullptr;
+  e->floors_h[floor].adj = nullptr;
+  e->floors_dirty = true;
+  if (!adj) return CITAM_OK;
+  if (n_spaces != e->floors_h[floor].n_spaces)
+    return fail(CITAM_ERR_INVALID, "adjacency is %d spaces, floor table has %d (load the table first)", n_spaces,
+                e->floors_h[floor].n_spaces);
+  size_t bits = (size_t)n_spaces * n_spaces, words = (bits + 31) / 32;
+  std::vector<uint32_t> w(std::max<size_t>(1, words), 0u);
+  for (size_t i = 0; i < bits; ++i)
+    if (adj[i]) w[i >> 5] |= 1u << (i & 31);
+  CK(cudaMalloc(&e->adj_d[floor], sizeof(uint32_t) * w.size()));
+  CK(cudaMemcpyAsync(e->adj_d[floor], w.data(), sizeof(uint32_t) * w.size(), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->floors_h[floor].adj = e->adj_d[floor];
+  return CITAM_OK;
+}
+
+int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_segment* segs, int64_t n_segs) {
+  if (!e || !seg_off || (n_segs > 0 && !segs)) return fail(CITAM_ERR_INVALID, "null argument");
+  if (seg_off[0] != 0 || seg_off[e->N] != n_segs) return fail(CITAM_ERR_INVALID, "seg_off must run from 0 to n_segs");
+  CK(cudaSetDevice(e->device));
+  cudaFree(e->segs_d); cudaFree(e->seg_off_d);
+  e->segs_d = nullptr; e->seg_off_d = nullptr; e->have_itin = false;
+  citam_segment* raw = nullptr;
+  CK(cudaMalloc(&e->segs_d, sizeof(int4) * std::max<int64_t>(1, n_segs)));
+  CK(cudaMalloc(&e->seg_off_d, sizeof(long long) * ((size_t)e->N + 1)));
+  CK(cudaMalloc(&raw, sizeof(citam_segment) * std::max<int64_t>(1, n_segs)));
+  CK(cudaMemcpyAsync(e->seg_off_d, seg_off, sizeof(long long) * ((size_t)e->N + 1), cudaMemcpyHostToDevice, e->stream));
+  if (n_segs) {
+    CK(cudaMemcpyAsync(raw, segs, sizeof(citam_segment) * n_segs, cudaMemcpyHostToDevice, e->stream));
+    Timed tm(e, CITAM_K_MISC);
+    k_repack_segments<<<(unsigned)((n_segs + 255) / 256), 256, 0, e->stream>>>(raw, n_segs, e->segs_d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(raw);
+  e->n_segs = n_segs;
+  e->have_itin = true;
+  return CITAM_OK;
+}
+
+int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
+  if (!e) return fail(CITAM_ERR_INVALID, "null engine");
+  if (!e->have_itin) return fail(CITAM_ERR_STATE, "citam_run before citam_load_itineraries");
+  if (t_begin < 0 || t_end < t_begin || t_end > (1 << 24)) return fail(CITAM_ERR_INVALID, "bad step range");
+  if (t_end == t_begin) return CITAM_OK;
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_ready(e, 1);  // uploads floor descriptors so pick_chunk sees the grid
+  if (rc) return rc;
+  int S = pick_chunk(e, t_end - t_begin);
+  rc = ensure_ready(e, S);
+  if (rc) return rc;
+  Params p = make_params(e);
+  for (int tb = t_begin; tb < t_end; tb += S) {
+    int steps = std::min(S, t_end - tb);
+    int rows = steps + 1;  // + halo row for step tb-1
+    CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride * steps, e->stream));
+    {
+      Timed tm(e, CITAM_K_EXPAND_BIN);
+      dim3 g((e->N + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
+      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb - 1, rows, 1);
+    }
+    CK(cudaGetLastError());
+    rc = run_sorted_stages(e, tb, steps);
+    if (rc) return rc;
+    e->agent_steps += (unsigned long long)steps * e->N;
+  }
+  e->prev_step = LLONG_MIN;
+  return CITAM_OK;
+}
+
+int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* states) {
+  if (!e || !states) return fail(CITAM_ERR_INVALID, "null argument");
+  if (step < 0) return fail(CITAM_ERR_INVALID, "negative step");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_ready(e, 1);
+  if (rc) return rc;
+  size_t n = (size_t)e->N;
+  int g = (e->N + 255) / 256;
+  CK(cudaMemcpyAsync(e->states_d, states, sizeof(citam_agent_state) * n, cudaMemcpyHostToDevice, e->stream));
+  if (e->prev_step == (long long)step - 1) {
+    CK(cudaMemcpyAsync(e->rec_x, e->prev_x, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->rec_y, e->prev_y, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->rec_fl, e->prev_fl, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+  } else {
+    k_fill_inactive<<<g, 256, 0, e->stream>>>(e->rec_x, e->rec_y, e->rec_fl, e->N);
+    e->launches++;
+  }
+  k_states_to_rec<<<g, 256, 0, e->stream>>>(e->states_d, e->N, e->rec_x + n, e->rec_y + n, e->rec_fl + n);
+  e->launches++;
+  CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_EXPAND_BIN);
+    k_bin_states<<<dim3(g, 1), 256, 0, e->stream>>>(p, 2);
+  }
+  CK(cudaGetLastError());
+  rc = run_sorted_stages(e, step, 1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->prev_x, e->rec_x + n, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->prev_y, e->rec_y + n, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->prev_fl, e->rec_fl + n, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+  e->prev_step = step;
+  e->agent_steps += e->N;
+  return check_overflow(e);
+}
+
+int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  if (!e->have_itin) return fail(CITAM_ERR_STATE, "no itineraries loaded");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_ready(e, 1);
+  if (rc) return rc;
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_MISC);
+    dim3 g((e->N + 127) / 128, 1);
+    k_expand_bin<<<g, 128, 0, e->stream>>>(p, step, 1, 0);
+    k_rec_to_states<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->rec_x, e->rec_y, e->rec_fl, e->N, e->states_d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->states_d, sizeof(citam_agent_state) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->prev_step = LLONG_MIN;
+  return CITAM_OK;
+}
+
+int citam_get_counters(citam_engine* e, citam_counters* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  DevCounters c;
+  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  out->agent_steps = e->agent_steps;
+  out->pair_tests = c.pair_tests;
+  out->contact_steps = c.contact_steps;
+  out->kernel_launches = e->launches;
+  out->pair_slots_used = c.pair_used;
+  out->coord_slots_used = c.coord_used;
+  out->log_records = std::min<unsigned long long>(c.log_count, e->log_cap);
+  out->overflow = c.overflow;
+  return CITAM_OK;
+}
+
+int citam_pair_count(citam_engine* e, uint64_t* n) {
+  citam_counters c;
+  int rc = citam_get_counters(e, &c);
+  if (rc) return rc;
+  rc = check_overflow(e);
+  if (rc) return rc;
+  *n = c.pair_slots_used;
+  return CITAM_OK;
+}
+
+int citam_coord_count(citam_engine* e, uint64_t* n) {
+  citam_counters c;
+  int rc = citam_get_counters(e, &c);
+  if (rc) return rc;
+  *n = c.coord_slots_used;
+  return CITAM_OK;
+}
+
+int citam_export_pairs(citam_engine* e, citam_pair* out, uint64_t capacity, uint64_t* n) {
+  if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  uint64_t have = 0;
+  rc = citam_pair_count(e, &have);
+  if (rc) return rc;
+  *n = have;
+  if (have == 0) return CITAM_OK;
+  if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu pairs, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
+  citam_pair* tmp = nullptr;
+  CK(cudaMalloc(&tmp, sizeof(citam_pair) * have));
+  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_compact_pairs<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, tmp, have, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, tmp, sizeof(citam_pair) * have, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(tmp);
+  // first-contact order = dict insertion order of the reference (contacts.py:135-142;
+  // pairs of one step are visited row-major, close_contacts_calculator.py:104-124)
+  std::sort(out, out + have, [](const citam_pair& a, const citam_pair& b) {
+    if (a.first_step != b.first_step) return a.first_step < b.first_step;
+    if (a.a1 != b.a1) return a.a1 < b.a1;
+    return a.a2 < b.a2;
+  });
+  return CITAM_OK;
+}
+
+int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, uint64_t* n) {
+  if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  uint64_t have = 0;
+  rc = citam_coord_count(e, &have);
+  if (rc) return rc;
+  *n = have;
+  if (have == 0) return CITAM_OK;
+  if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu coords, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
+  citam_coord* tmp = nullptr;
+  CK(cudaMalloc(&tmp, sizeof(citam_coord) * have));
+  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_compact_coords<<<(unsigned)((e->coord_cap + 255) / 256), 256, 0, e->stream>>>(e->coords, e->coord_cap, tmp, have, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, tmp, sizeof(citam_coord) * have, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(tmp);
+  std::sort(out, out + have, [](const citam_coord& a, const citam_coord& b) {
+    if (a.floor != b.floor) return a.floor < b.floor;
+    if (a.sx != b.sx) return a.sx < b.sx;
+    return a.sy < b.sy;
+  });
+  return CITAM_OK;
+}
+
+int citam_export_agent_durations(citam_engine* e, uint64_t* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  std::vector<uint32_t> tmp((size_t)e->N);
+  CK(cudaMemcpyAsync(tmp.data(), e->agent_dur, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i];
+  return CITAM_OK;
+}
+
+int citam_export_contact_log(citam_engine* e, citam_contact* out, uint64_t capacity, uint64_t* n) {
+  if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  citam_counters c;
+  rc = citam_get_counters(e, &c);
+  if (rc) return rc;
+  *n = c.log_records;
+  if (c.log_records == 0) return CITAM_OK;
+  if (capacity < c.log_records) return fail(CITAM_ERR_CAPACITY, "output holds %llu records, %llu needed", (unsigned long long)capacity, (unsigned long long)c.log_records);
+  CK(cudaMemcpyAsync(out, e->log, sizeof(citam_contact) * c.log_records, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  // deterministic order: (step, a1, a2) == the order the reference visits contacts
+  std::sort(out, out + c.log_records, [](const citam_contact& a, const citam_contact& b) {
+    if (a.step != b.step) return a.step < b.step;
+    if (a.a1 != b.a1) return a.a1 < b.a1;
+    return a.a2 < b.a2;
+  });
+  return CITAM_OK;
+}
+
+int citam_statistics(citam_engine* e, citam_stats* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  size_t n = (size_t)e->N;
+  CK(cudaMemsetAsync(e->agent_nev, 0, 4 * n, e->stream));
+  CK(cudaMemsetAsync(e->agent_has, 0, 4 * n, e->stream));
+  CK(cudaMemsetAsync(e->ctr_d->stats, 0, sizeof(unsigned long long) * 6, e->stream));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_stats_pairs<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, e->agent_nev, e->agent_has, e->ctr_d);
+    k_stats_agents<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->agent_nev, e->agent_has, e->N, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  DevCounters c;
+  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  out->total_duration = c.stats[0];
+  out->n_pairs = c.stats[1];
+  out->n_agents_with_contacts = c.stats[2];
+  out->sum_events_per_agent = c.stats[3];
+  out->max_events_per_agent = c.stats[4];
+  out->reserved = 0;
+  return CITAM_OK;
+}
+
+int citam_get_timings(citam_engine* e, citam_timings* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  drain_timings(e);
+  for (int k = 0; k < CITAM_N_KERNELS; ++k) { out->ms[k] = e->t_ms[k]; out->launches[k] = e->t_n[k]; }
+  return CITAM_OK;
+}
+
+int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements) {
+  if (!e || !ptr || !n_elements) return fail(CITAM_ERR_INVALID, "null argument");
+  *ptr = e->agent_dur;
+  *n_elements = (uint64_t)e->N;
+  return CITAM_OK;
+}
+
+int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n) {
+  if (!e || (n && !pairs)) return fail(CITAM_ERR_INVALID, "null argument");
+  if (!n) return CITAM_OK;
+  CK(cudaSetDevice(e->device));
+  for (uint64_t i = 0; i < n; ++i)
+    if (pairs[i].a1 >= pairs[i].a2 || pairs[i].a2 >= (uint32_t)e->N) return fail(CITAM_ERR_INVALID, "bad pair record %llu", (unsigned long long)i);
+  citam_pair* tmp = nullptr;
+  CK(cudaMalloc(&tmp, sizeof(citam_pair) * n));
+  CK(cudaMemcpyAsync(tmp, pairs, sizeof(citam_pair) * n, cudaMemcpyHostToDevice, e->stream));
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_merge_pairs<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, tmp, n);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(tmp);
+  return check_overflow(e);
+}
+
+int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n) {
+  if (!e || (n && !coords)) return fail(CITAM_ERR_INVALID, "null argument");
+  if (!n) return CITAM_OK;
+  CK(cudaSetDevice(e->device));
+  citam_coord* tmp = nullptr;
+  CK(cudaMalloc(&tmp, sizeof(citam_coord) * n));
+  CK(cudaMemcpyAsync(tmp, coords, sizeof(citam_coord) * n, cudaMemcpyHostToDevice, e->stream));
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_merge_coords<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, tmp, n);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(tmp);
+  return check_overflow(e);
+}
+
+}  // extern "C"

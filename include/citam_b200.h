@@ -1,0 +1,219 @@
+/*
+ * citam_b200.h — C ABI of the B200-native CITAM step loop.
+ *
+ * The upstream reference (corning-incorporated/citam) is pure Python and has no
+ * FFI: its hot path is reached through the `Calculator` plugin ABC
+ * (citam/engine/calculators/calculator.py:9-33) and `Simulation.run_serial`
+ * (citam/engine/core/simulation.py:215-275).  This header is the boundary a
+ * maintainer would bind from that Python code with ctypes;
+ * every entry point names the reference code it replaces.
+ *
+ * Conventions: plain C, opaque handle, every call returns 0 on success or a
+ * negative citam_status; `citam_last_error()` gives the message of the last
+ * failing call on this thread.  All pointers are caller-owned HOST buffers
+ * unless a name ends in `_device`.  One engine is bound to one GPU; calls on
+ * one engine are not thread-safe.  Work is enqueued on the engine's stream
+ * (`citam_set_stream`, default: the legacy default stream) and calls that
+ * return data synchronise that stream.
+ *
+ * There is no CPU fallback: `citam_create` fails when no sm_100 device is
+ * usable.
+ */
+#ifndef CITAM_B200_H
+#define CITAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CITAM_ABI_VERSION 1
+
+typedef enum {
+  CITAM_OK = 0,
+  CITAM_ERR_INVALID = -1,   /* bad argument                                  */
+  CITAM_ERR_CUDA = -2,      /* CUDA runtime error (message has the detail)   */
+  CITAM_ERR_CAPACITY = -3,  /* a device table overflowed; enlarge and re-run */
+  CITAM_ERR_STATE = -4,     /* call order (e.g. run before load)             */
+  CITAM_ERR_NO_DEVICE = -5  /* no usable CUDA device                         */
+} citam_status;
+
+typedef struct citam_engine citam_engine;
+
+/* ---- configuration ---------------------------------------------------- */
+typedef struct {
+  int32_t n_agents;         /* agents 0..n-1 in schedule order (simulation.py:277-289) */
+  int32_t n_floors;
+  double contact_distance;  /* CloseContactsCalculator.contact_distance, strict `<`
+                               (close_contacts_calculator.py:21-28,171)                */
+  int32_t cell_size;        /* uniform-grid cell edge in drawing units; 0 = ceil(D)    */
+  int32_t device;           /* CUDA device ordinal                                     */
+  uint64_t pair_capacity;   /* slots of the per-pair table (rounded up to 2^k); 0=auto */
+  uint64_t coord_capacity;  /* slots of the per-coordinate histogram; 0 = auto         */
+  uint64_t log_capacity;    /* contact-log records kept for the full-fidelity writers
+                               (contacts.txt, raw_contact_data.ccd); 0 = log off       */
+  int32_t steps_per_chunk;  /* time steps processed per launch group; 0 = auto         */
+  int32_t flags;            /* CITAM_FLAG_*                                            */
+} citam_config;
+
+#define CITAM_FLAG_TIMING 1 /* record CUDA events around every kernel (citam_get_timings) */
+
+/* One constant-velocity run of an itinerary.  Agent a's position for
+ * t in [t0, next.t0) is (x0 + dx*(t-t0), y0 + dy*(t-t0)) on `floor`; before the
+ * first segment the agent is not in the facility; the last segment lasts for
+ * ever (the reference's sticky tail: agent.py:77-107 with
+ * office_schedule.py:632-638).  Produced by citam_b200.itinerary.encode(). */
+typedef struct {
+  int32_t t0;
+  int32_t x0, y0;
+  int16_t dx, dy;
+  int16_t floor;
+  int16_t reserved;
+} citam_segment;
+
+/* Per-agent state at one step; what Agent.pos / current_floor /
+ * current_location hold (agent.py:63-65).  floor < 0: not in the facility
+ * (pos None); loc < 0: inside no space (current_location None). */
+typedef struct {
+  int32_t x, y;
+  int16_t floor;
+  int16_t loc;
+} citam_agent_state;
+
+/* One space of a floor for the location-table builder (Space, space.py:25-117). */
+typedef struct {
+  int32_t bb_xmin, bb_xmax, bb_ymin, bb_ymax; /* round() of space.path.bbox() (space.py:209-216) */
+  int32_t seg_begin, seg_end;                 /* range in the floor's boundary-segment array      */
+  int32_t door_begin, door_end;               /* range in the floor's door array; empty when the
+                                                 door shortcut does not apply (space.py:218-224)  */
+} citam_space;
+
+/* One boundary segment: endpoints, the unit normal the reference compares
+ * against (svgpathtools Line.normal, geometry.py:580) and whether
+ * length() > 1.0 (space.py:189). */
+typedef struct {
+  double sx, sy, ex, ey;
+  double nx, ny;
+  int32_t long_enough;
+  int32_t reserved;
+} citam_boundary;
+
+typedef struct {
+  double sx, sy, ex, ey;
+} citam_door;
+
+typedef struct {
+  uint32_t a1, a2;       /* a1 < a2                                               */
+  uint32_t first_step;   /* step of the first contact: row order of pair_contact.csv */
+  uint32_t n_events;     /* len(contact_data[key])            (contacts.py:170)   */
+  uint64_t duration;     /* sum of event durations            (contacts.py:171-172) */
+} citam_pair;
+
+typedef struct {
+  int32_t floor;
+  int32_t sx, sy;        /* x1+x2, y1+y2: twice the contact position (close_contacts_calculator.py:218-220) */
+  int32_t reserved;
+  uint64_t count;
+} citam_coord;
+
+typedef struct {
+  uint32_t step, a1, a2; /* one contact-step; a1 < a2 */
+} citam_contact;
+
+/* Integer sums behind ContactEvents.extract_statistics (contacts.py:185-294);
+ * the host does the final float division/rounding exactly as Python does. */
+typedef struct {
+  uint64_t total_duration;      /* sum over pairs of duration                          */
+  uint64_t n_pairs;             /* == sum(n_others.values())                           */
+  uint64_t n_agents_with_contacts;
+  uint64_t sum_events_per_agent;/* sum over agents of their n_events (== 2*sum n_events) */
+  uint64_t max_events_per_agent;
+  uint64_t reserved;
+} citam_stats;
+
+typedef struct {
+  uint64_t agent_steps;   /* agent-steps advanced (N * steps)                     */
+  uint64_t pair_tests;    /* distance evaluations                                 */
+  uint64_t contact_steps; /* contacts found                                       */
+  uint64_t kernel_launches;
+  uint64_t pair_slots_used, coord_slots_used, log_records;
+  uint64_t overflow;      /* bit0 pair table, bit1 coord table, bit2 log          */
+} citam_counters;
+
+#define CITAM_N_KERNELS 8
+typedef struct {
+  double ms[CITAM_N_KERNELS];      /* summed CUDA-event time per kernel kind */
+  uint64_t launches[CITAM_N_KERNELS];
+} citam_timings;
+/* kernel kinds (index into citam_timings) */
+#define CITAM_K_EXPAND_BIN 0
+#define CITAM_K_SCAN 1
+#define CITAM_K_SCATTER 2
+#define CITAM_K_PAIRS 3
+#define CITAM_K_LUT 4
+#define CITAM_K_FINALIZE 5
+#define CITAM_K_MISC 6
+
+/* ---- life cycle -------------------------------------------------------- */
+int citam_abi_version(void);
+const char* citam_last_error(void);
+int citam_create(const citam_config* cfg, citam_engine** out);
+void citam_destroy(citam_engine* e);
+int citam_set_stream(citam_engine* e, void* cuda_stream);
+
+/* ---- facility: replaces Floorplan.identify_this_location + hallway test -- */
+/* Build floor `f`'s (x,y)->space table on the device with the reference's rule
+ * (floorplan.py:215-241, space.py:194-280, geometry.py:31-127,558-588) over the
+ * lattice [minx, minx+W) x [miny, miny+H). */
+int citam_build_floor_lut(citam_engine* e, int32_t floor, int32_t minx, int32_t miny,
+                          int32_t W, int32_t H, int32_t n_spaces, const citam_space* spaces,
+                          int32_t n_boundaries, const citam_boundary* boundaries,
+                          int32_t n_doors, const citam_door* doors);
+/* Or install a table computed elsewhere (int16 [H][W], -1 = no space). */
+int citam_set_floor_lut(citam_engine* e, int32_t floor, int32_t minx, int32_t miny,
+                        int32_t W, int32_t H, int32_t n_spaces, const int16_t* lut);
+int citam_get_floor_lut(citam_engine* e, int32_t floor, int16_t* out /* [H*W] */);
+/* adj[a*n_spaces+b] != 0  <=>  both spaces are hallways and the floor's hallway
+ * graph has the edge (close_contacts_calculator.py:173-203); NULL = no graph. */
+int citam_set_floor_adjacency(citam_engine* e, int32_t floor, int32_t n_spaces, const uint8_t* adj);
+
+/* ---- itineraries: replaces Schedule.itinerary / get_next_position ------- */
+int citam_load_itineraries(citam_engine* e, const int64_t* seg_off /* [n_agents+1] */,
+                           const citam_segment* segs, int64_t n_segs);
+
+/* ---- the step loop: replaces Simulation.step x (t_end - t_begin) --------- */
+/* Advance every agent through steps [t_begin, t_end) and accumulate contacts
+ * (simulation.py:291-361 + close_contacts_calculator.py:64-137).  Accumulators
+ * are commutative, so ranges may be run in any order / on different engines. */
+int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end);
+/* One step on caller-supplied states (the Calculator.run(current_step, agents)
+ * entry: calculator.py:24-25).  `states` has n_agents records. */
+int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* states);
+/* Agent states at one step from the loaded itineraries (trajectory writer,
+ * simulation.py:312-334). */
+int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out /* [n_agents] */);
+int citam_reset(citam_engine* e); /* clear all accumulators, keep facility + itineraries */
+
+/* ---- results: replaces ContactEvents / extract_* ------------------------ */
+int citam_pair_count(citam_engine* e, uint64_t* n);
+int citam_export_pairs(citam_engine* e, citam_pair* out, uint64_t capacity, uint64_t* n);
+int citam_export_agent_durations(citam_engine* e, uint64_t* out /* [n_agents] */);
+int citam_coord_count(citam_engine* e, uint64_t* n);
+int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, uint64_t* n);
+int citam_export_contact_log(citam_engine* e, citam_contact* out, uint64_t capacity, uint64_t* n);
+int citam_statistics(citam_engine* e, citam_stats* out);
+int citam_get_counters(citam_engine* e, citam_counters* out);
+int citam_get_timings(citam_engine* e, citam_timings* out);
+
+/* Device views for the multi-GPU reduction (torch.distributed/NCCL all-reduce
+ * straight on engine memory): per-agent contact seconds, uint32 [n_agents]. */
+int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements);
+/* Merge pair / coordinate records exported by another engine (other rank). */
+int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n);
+int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITAM_B200_H */
