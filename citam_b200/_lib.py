@@ -15,8 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libcitam_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
 FLAG_TIMING = 1
+FLAG_HASHED_COORDS = 2
 N_KERNELS = 8
-KERNEL_NAMES = ["expand_bin", "scan", "scatter", "pairs", "lut", "finalize", "misc", "unused"]
+KERNEL_NAMES = ["expand_bin", "scan", "scatter", "pairs", "lut", "finalize", "misc", "accumulate"]
 
 
 class CitamDeviceError(RuntimeError):

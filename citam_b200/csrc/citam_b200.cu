@@ -14,9 +14,11 @@
 //   k_scan        per-step exclusive scan of the cell histogram, staged in shared memory
 //   k_scatter     counting-sort scatter into cell order (16-byte records)
 //   k_pairs       half-neighbourhood pair test (own cell tail + right cell + 3 cells of the
-//                 row above) with the reference's float64 predicate, then accumulation into
-//                 the per-pair hash table, per-agent counters, per-coordinate histogram and
-//                 the optional contact log
+//                 row above) with the reference's float64 predicate, then accumulation: one
+//                 64-bit atomic into the 16-byte per-pair entry (duration | events<<32), one
+//                 64-bit reduction into the dense per-coordinate histogram, and the optional
+//                 contact log.  Per-agent contact seconds are derived from the pair table at
+//                 export time (sum over the agent's pairs), not counted per contact.
 // All of this is HBM/L2-bound integer work; there is no GEMM in the path.
 
 #include "../../include/citam_b200.h"
@@ -68,22 +70,40 @@ struct FloorDev {
   int32_t n_spaces;
   const int16_t* lut;   // [H][W] space index, -1 = none; NULL = floor not loaded
   const uint32_t* adj;  // n_spaces*n_spaces bits, NULL = no hallway graph
+  long long hist_base;  // first bucket of this floor in the dense coordinate histogram
+  int32_t hist_w, hist_h;  // (2W-1) x (2H-1) half-unit buckets: contact positions are midpoints
 };
 
+// One slot of the per-pair table: 16 bytes, two per 32-byte sector.  `acc` packs everything the
+// reference keeps per pair (contacts.py:155-183) so that one compare-and-swap on the sector the
+// probe already fetched applies a whole update:
+//   bits  0-23  contact-steps (sum of event durations)        < 2^24 = the step-range limit
+//   bits 24-39  number of events                              < 2^16
+//   bits 40-63  0xFFFFFF - first contact step (max-reduced; 0 = none yet)
 struct __align__(16) PairEntry {
   unsigned long long key;  // (a1 << 32) | a2 with a1 < a2, 0 = empty
-  uint32_t dur;            // contact-steps
-  uint32_t nev;            // events (contact at t and not at t-1)
-  uint32_t first_inv;      // 0xFFFFFFFF - first contact step (max-reduced; 0 = none)
-  uint32_t pad0;
-  unsigned long long pad1;
+  unsigned long long acc;
 };
-static_assert(sizeof(PairEntry) == 32, "one 32-byte sector per pair entry");
+static_assert(sizeof(PairEntry) == 16, "two pair entries per 32-byte sector");
+#define ACC_DUR(a) ((uint32_t)((a) & 0xffffffULL))
+#define ACC_NEV(a) ((uint32_t)(((a) >> 24) & 0xffffULL))
+#define ACC_FIRST_INV(a) ((uint32_t)((a) >> 40))
+#define NO_STEP 0xFFFFFFFFu
 
 struct __align__(16) CoordEntry {
   unsigned long long key;  // bit63 | floor<<56 | (sx+2^27)<<28 | (sy+2^27); 0 = empty
   unsigned long long count;
 };
+
+// One detected contact run, appended by k_pairs and applied by k_accumulate.
+struct __align__(16) ContactRec {
+  uint32_t a1, a2;   // a1 < a2
+  uint32_t t_run;    // step (24 bits) | (run - 1) << 24
+  uint32_t bucket;   // dense-histogram bucket (30 bits) | bit 31: in contact at t-1 is already known
+};
+
+constexpr int kSubBuffers = 64;    // the contact buffer is split so that appends do not all hit one counter
+constexpr int kCounterStride = 16;  // 128 bytes between sub-buffer counters
 
 struct DevCounters {
   unsigned long long pair_tests;
@@ -94,6 +114,8 @@ struct DevCounters {
   unsigned long long overflow;
   unsigned long long export_cursor;
   unsigned long long stats[6];
+  unsigned long long pad[3];
+  unsigned long long cbuf_count[kSubBuffers * kCounterStride];
 };
 
 struct Params {
@@ -105,19 +127,19 @@ struct Params {
   const FloorDev* floors;
   const int4* segs;  // {t0 | floor<<24, x0, y0, dx&0xffff | dy<<16}
   const long long* seg_off;
-  int32_t* rec_x;  // [(S+1)][N]  row 0 = halo step t_begin-1
-  int32_t* rec_y;
-  int32_t* rec_fl;  // floor<<16 | (loc & 0xffff); floor -1 = not in the facility
-  uint32_t* rank;   // [S][N]
+  int4* rec;        // [(S+1)][N] {x, y, state word, rank in cell}; row 0 = halo step t_begin-1
   uint32_t* cells;  // [S][cells_stride]
-  int4* sorted;     // [S][N] {x, y, agent, floor<<16|loc}
+  int4* sorted;     // [S][N] {x, y, agent, state word} in cell order
   PairEntry* pairs;
   unsigned long long pair_mask;
-  CoordEntry* coords;
+  CoordEntry* coords;     // hashed histogram (lattices too large for the dense one)
   unsigned long long coord_mask;
+  unsigned long long* hist;  // dense histogram, NULL = use the hash
+  int32_t range_begin;       // first step of the current citam_run range
   citam_contact* log;
   unsigned long long log_cap;
-  uint32_t* agent_dur;
+  ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
+  unsigned long long cbuf_sub_cap;
   DevCounters* ctr;
 };
 
@@ -125,12 +147,24 @@ struct Params {
 #define OVF_COORD 2ULL
 #define OVF_LOG 4ULL
 #define OVF_GRID 8ULL
+#define OVF_FIELD 16ULL
 
-__device__ __forceinline__ int32_t pack_fl(int floor, int loc) {
-  return (int32_t)(((uint32_t)floor << 16) | ((uint32_t)loc & 0xffffu));
+// state word: bits 0-14 space index (0x7fff = none); bit 15 "changed": the agent is NOT known to
+// be exactly where it was one step earlier (it moves, or this is the first step of its
+// segment); bits 16-23 "stay": for how many following steps of this chunk the state is
+// guaranteed identical (same zero-velocity segment); bits 24-30 floor; bit 31 = not in the
+// facility.  changed/stay come from the segment store alone, so they agree with each other:
+// changed(t+k) == 0 for k = 1..stay(t) and changed(t+stay+1) == 1 (or the chunk ends).
+constexpr int kMaxChunk = 256;  // stay must fit 8 bits
+__device__ __forceinline__ int32_t pack_fl(int floor, int loc, int changed = 1, int stay = 0) {
+  if (floor < 0) return (int32_t)0x8000ffffu;
+  return (int32_t)(((uint32_t)(floor & 0x7f) << 24) | ((uint32_t)(stay & 0xff) << 16) | ((uint32_t)(changed & 1) << 15) |
+                   ((uint32_t)loc & 0x7fffu));
 }
-__device__ __forceinline__ int fl_floor(int32_t fl) { return fl >> 16; }
-__device__ __forceinline__ int fl_loc(int32_t fl) { return (int)(int16_t)(fl & 0xffff); }
+__device__ __forceinline__ int fl_floor(int32_t fl) { return fl < 0 ? -1 : (fl >> 24) & 0x7f; }
+__device__ __forceinline__ int fl_loc(int32_t fl) { int v = fl & 0x7fff; return v == 0x7fff ? -1 : v; }
+__device__ __forceinline__ bool fl_changed(int32_t fl) { return (fl >> 15) & 1; }
+__device__ __forceinline__ int fl_stay(int32_t fl) { return (fl >> 16) & 0xff; }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33;
@@ -157,7 +191,7 @@ __device__ __forceinline__ int cell_of(const FloorDev& fd, int cell, int x, int 
 // K1a: itinerary expansion + grid histogram.
 // One thread walks one agent through kRowsPerThread consecutive steps: the segment cursor
 // advances monotonically, the location table is touched only when the position changes, and
-// every store is coalesced over the 32 agents of a warp.
+// every 16-byte record store is coalesced over the 32 agents of a warp.
 // --------------------------------------------------------------------------
 constexpr int kRowsPerThread = 16;
 
@@ -191,9 +225,7 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
     }
     size_t o = (size_t)row * p.N + a;
     if (c < sb || t < 0) {
-      p.rec_x[o] = 0;
-      p.rec_y[o] = 0;
-      p.rec_fl[o] = pack_fl(-1, -1);
+      p.rec[o] = make_int4(0, 0, pack_fl(-1, -1), 0);
       continue;
     }
     int dt = t - (s.x & 0xffffff);
@@ -204,14 +236,16 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
       loc = (f < p.F) ? lut_lookup(p.floors[f], x, y) : -1;
       lastx = x; lasty = y; lastf = f;
     }
-    p.rec_x[o] = x;
-    p.rec_y[o] = y;
-    p.rec_fl[o] = pack_fl(f, loc);
+    // stationary inside one segment: same state as the step before / for `stay` more steps
+    const bool still = s.w == 0;
+    int changed = !(still && dt >= 1);
+    int stay = still ? min(min(next_t0 - 1 - t, rows - 1 - row), kMaxChunk - 1) : 0;
+    uint32_t rk = 0;
     if (do_bin && row >= 1 && loc >= 0) {
       int key = cell_of(p.floors[f], p.cell, x, y);
-      uint32_t rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
-      p.rank[(size_t)(row - 1) * p.N + a] = rk;
+      rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
     }
+    p.rec[o] = make_int4(x, y, pack_fl(f, loc, changed, stay), (int)rk);
   }
 }
 
@@ -221,47 +255,46 @@ __global__ void k_bin_states(Params p, int rows) {
   int row = blockIdx.y + 1;
   if (a >= p.N || row >= rows) return;
   size_t o = (size_t)row * p.N + a;
-  int32_t fl = p.rec_fl[o];
-  int f = fl_floor(fl), loc = fl_loc(fl);
+  int4 r = p.rec[o];
+  int f = fl_floor(r.z), loc = fl_loc(r.z);
   if (f < 0 || loc < 0) return;
-  int x = p.rec_x[o], y = p.rec_y[o];
   bool ok = f < p.F;
   if (ok) {
     const FloorDev& fd = p.floors[f];
-    int fx = x - fd.minx, fy = y - fd.miny;
+    int fx = r.x - fd.minx, fy = r.y - fd.miny;
     ok = fd.lut != nullptr && (unsigned)fx < (unsigned)fd.W && (unsigned)fy < (unsigned)fd.H;
   }
   if (!ok) {  // caller says "located" but the point is outside the floor's grid
     atomicOr(&p.ctr->overflow, OVF_GRID);
-    p.rec_fl[o] = pack_fl(f, -1);
+    p.rec[o].z = pack_fl(f, -1);
     return;
   }
-  int key = cell_of(p.floors[f], p.cell, x, y);
-  uint32_t rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
-  p.rank[(size_t)(row - 1) * p.N + a] = rk;
+  int key = cell_of(p.floors[f], p.cell, r.x, r.y);
+  p.rec[o].w = (int)atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
 }
 
-__global__ void k_states_to_rec(const citam_agent_state* st, int N, int32_t* x, int32_t* y, int32_t* fl) {
+__global__ void k_states_to_rec(const citam_agent_state* st, int N, int4* rec) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= N) return;
   citam_agent_state s = st[a];
   int f = s.floor < 0 ? -1 : s.floor;
   int l = (f < 0 || s.loc < 0) ? -1 : s.loc;
-  x[a] = s.x; y[a] = s.y; fl[a] = pack_fl(f, l);
+  rec[a] = make_int4(s.x, s.y, pack_fl(f, l), 0);
 }
 
-__global__ void k_rec_to_states(const int32_t* x, const int32_t* y, const int32_t* fl, int N, citam_agent_state* st) {
+__global__ void k_rec_to_states(const int4* rec, int N, citam_agent_state* st) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= N) return;
+  int4 r = rec[a];
   citam_agent_state s;
-  s.x = x[a]; s.y = y[a]; s.floor = (int16_t)fl_floor(fl[a]); s.loc = (int16_t)fl_loc(fl[a]);
+  s.x = r.x; s.y = r.y; s.floor = (int16_t)fl_floor(r.z); s.loc = (int16_t)fl_loc(r.z);
   st[a] = s;
 }
 
-__global__ void k_fill_inactive(int32_t* x, int32_t* y, int32_t* fl, int N) {
+__global__ void k_fill_inactive(int4* rec, int N) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= N) return;
-  x[a] = 0; y[a] = 0; fl[a] = pack_fl(-1, -1);
+  rec[a] = make_int4(0, 0, pack_fl(-1, -1), 0);
 }
 
 // --------------------------------------------------------------------------
@@ -324,14 +357,12 @@ __global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   int row = blockIdx.y;
   if (a >= p.N || row >= rows) return;
-  size_t o = (size_t)(row + 1) * p.N + a;
-  int32_t fl = p.rec_fl[o];
-  int f = fl_floor(fl), loc = fl_loc(fl);
+  int4 r = p.rec[(size_t)(row + 1) * p.N + a];
+  int f = fl_floor(r.z), loc = fl_loc(r.z);
   if (f < 0 || loc < 0) return;
-  int x = p.rec_x[o], y = p.rec_y[o];
-  int key = cell_of(p.floors[f], p.cell, x, y);
-  uint32_t dest = p.cells[(size_t)row * p.cells_stride + key] + p.rank[(size_t)row * p.N + a];
-  p.sorted[(size_t)row * p.N + dest] = make_int4(x, y, a, fl);
+  int key = cell_of(p.floors[f], p.cell, r.x, r.y);
+  uint32_t dest = p.cells[(size_t)row * p.cells_stride + key] + (uint32_t)r.w;
+  p.sorted[(size_t)row * p.N + dest] = make_int4(r.x, r.y, a, r.z);
 }
 
 // --------------------------------------------------------------------------
@@ -359,35 +390,60 @@ __device__ __forceinline__ bool within(int dx, int dy, double D) {
   return __dsqrt_rn((double)s) < D;
 }
 
-__device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32_t a2, uint32_t t,
-                                            uint32_t add_dur, uint32_t add_nev) {
-  unsigned long long key = ((unsigned long long)a1 << 32) | a2;
+// Linear probing is bounded: a table that needs more probes than this is reported as full
+// (CITAM_ERR_CAPACITY) instead of degrading into a scan of the whole table.
+constexpr int kMaxProbes = 256;
+
+// Find or insert the pair's slot.  Returns the slot index, or ~0 when the table is full.
+__device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigned long long key) {
   unsigned long long h = mix64(key) & p.pair_mask;
-  bool found = false;
-  for (unsigned long long probe = 0; probe <= p.pair_mask; ++probe) {
+  for (int probe = 0; probe < kMaxProbes; ++probe) {
     unsigned long long k = *(volatile unsigned long long*)&p.pairs[h].key;
-    if (k == key) { found = true; break; }
+    if (k == key) return h;
     if (k == 0ULL) {
       unsigned long long old = atomicCAS(&p.pairs[h].key, 0ULL, key);
-      if (old == 0ULL) { atomicAdd(&p.ctr->pair_used, 1ULL); found = true; break; }
-      if (old == key) { found = true; break; }
+      if (old == 0ULL) { atomicAdd(&p.ctr->pair_used, 1ULL); return h; }
+      if (old == key) return h;
     }
     h = (h + 1) & p.pair_mask;
   }
-  if (!found) { atomicOr(&p.ctr->overflow, OVF_PAIR); return; }
-  atomicAdd(&p.pairs[h].dur, add_dur);
-  if (add_nev) atomicAdd(&p.pairs[h].nev, add_nev);
-  // min over every contact step seen by this engine, so partial ranges / merged shards agree
-  atomicMax(&p.pairs[h].first_inv, 0xFFFFFFFFu - t);
+  atomicOr(&p.ctr->overflow, OVF_PAIR);
+  return ~0ULL;
+}
+
+// add_dur contact-steps and add_nev events; `first` (a step, or NO_STEP) lowers the pair's
+// first-contact step.  The first contact of a pair is always an event start, so callers pass a
+// step only for event starts and for the first step of a run range.
+__device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32_t a2, uint32_t first,
+                                            unsigned long long add_dur, unsigned long long add_nev) {
+  unsigned long long key = ((unsigned long long)a1 << 32) | a2;
+  unsigned long long h = pair_slot(p, key);
+  if (h == ~0ULL) return;
+  unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
+  unsigned long long old = *(volatile unsigned long long*)&p.pairs[h].acc;
+  for (;;) {
+    unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
+    if (d > 0xffffffULL || n > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
+    unsigned long long f = max((unsigned long long)ACC_FIRST_INV(old), finv);
+    unsigned long long seen = atomicCAS(&p.pairs[h].acc, old, d | (n << 24) | (f << 40));
+    if (seen == old) return;
+    old = seen;
+  }
 }
 
 __device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx, int sy, unsigned long long add) {
+  if (p.hist != nullptr) {  // dense: one reduction, no probe
+    const FloorDev& fd = p.floors[floor];
+    long long ix = (long long)sx - 2LL * fd.minx, iy = (long long)sy - 2LL * fd.miny;
+    atomicAdd(p.hist + fd.hist_base + iy * fd.hist_w + ix, add);
+    return;
+  }
   unsigned long long key = (1ULL << 63) | ((unsigned long long)(floor & 0x7f) << 56) |
                            ((unsigned long long)((uint32_t)(sx + (1 << 27)) & 0xfffffffu) << 28) |
                            (unsigned long long)((uint32_t)(sy + (1 << 27)) & 0xfffffffu);
   unsigned long long h = mix64(key) & p.coord_mask;
   bool found = false;
-  for (unsigned long long probe = 0; probe <= p.coord_mask; ++probe) {
+  for (int probe = 0; probe < kMaxProbes; ++probe) {
     unsigned long long k = *(volatile unsigned long long*)&p.coords[h].key;
     if (k == key) { found = true; break; }
     if (k == 0ULL) {
@@ -403,27 +459,50 @@ __device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx,
 
 // Was the pair in contact at the previous step?  Full predicate on the halo/previous row
 // (contacts.py:131-133: an event continues iff last.start_step + last.duration == step).
+// One 16-byte record per agent: two sector reads.
 __device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
-  int32_t f1 = p.rec_fl[prow_off + a1], f2 = p.rec_fl[prow_off + a2];
-  int fl1 = fl_floor(f1), fl2 = fl_floor(f2);
-  int l1 = fl_loc(f1), l2 = fl_loc(f2);
+  int4 r1 = p.rec[prow_off + a1], r2 = p.rec[prow_off + a2];
+  int fl1 = fl_floor(r1.z), fl2 = fl_floor(r2.z);
+  int l1 = fl_loc(r1.z), l2 = fl_loc(r2.z);
   if (fl1 < 0 || fl1 != fl2 || l1 < 0 || l2 < 0) return false;
-  int x1 = p.rec_x[prow_off + a1], x2 = p.rec_x[prow_off + a2];
-  int y1 = p.rec_y[prow_off + a1], y2 = p.rec_y[prow_off + a2];
-  long long dx = (long long)x2 - x1, dy = (long long)y2 - y1;
+  long long dx = (long long)r2.x - r1.x, dy = (long long)r2.y - r1.y;
   long long lim = (long long)p.D + 1;
   if (dx > lim || dx < -lim || dy > lim || dy < -lim) return false;
   if (!within((int)dx, (int)dy, p.D)) return false;
   return loc_rule(p.floors[fl1], l1, l2);
 }
 
-__device__ __forceinline__ void on_contact(const Params& p, int row, uint32_t t, const int4& me, const int4& ot) {
+// A contact found at step t that lasts `run` steps (both agents provably stay put for run-1
+// more steps of this chunk): one table update for the whole run.
+__device__ __forceinline__ void on_contact(const Params& p, int row, uint32_t t, const int4& me, const int4& ot,
+                                           uint32_t run, int sub) {
   uint32_t a1 = (uint32_t)min(me.z, ot.z), a2 = (uint32_t)max(me.z, ot.z);
-  bool was = contact_prev(p, (size_t)row * p.N, a1, a2);  // rec row `row` holds step t-1
-  pair_upsert(p, a1, a2, t, 1u, was ? 0u : 1u);
-  atomicAdd(&p.agent_dur[a1], 1u);
-  atomicAdd(&p.agent_dur[a2], 1u);
-  coord_upsert(p, fl_floor(me.w), me.x + ot.x, me.y + ot.y, 1ULL);
+  // both agents exactly where (and what) they were one step ago: they were in contact then too;
+  // otherwise the predicate is evaluated on the previous row (rec row `row` holds step t-1)
+  const bool known = !fl_changed(me.w) && !fl_changed(ot.w);
+  const int floor = fl_floor(me.w);
+  if (p.cbuf != nullptr) {
+    // warp-aggregated append into the chunk's contact buffer; k_accumulate applies it
+    const FloorDev& fd = p.floors[floor];
+    long long ix = (long long)(me.x + ot.x) - 2LL * fd.minx, iy = (long long)(me.y + ot.y) - 2LL * fd.miny;
+    uint32_t bucket = (uint32_t)(fd.hist_base + iy * fd.hist_w + ix) | (known ? 0x80000000u : 0u);
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0)
+      base = atomicAdd(&p.ctr->cbuf_count[sub * kCounterStride], (unsigned long long)g.size());
+    base = g.shfl(base, 0) + g.thread_rank();
+    if (base < p.cbuf_sub_cap) {
+      ContactRec r;
+      r.a1 = a1; r.a2 = a2; r.t_run = (t & 0xffffffu) | ((run - 1u) << 24); r.bucket = bucket;
+      p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + base] = r;
+      return;
+    }
+    // sub-buffer full: fall through and accumulate inline (k_accumulate clamps the count)
+  }
+  bool was = known ? true : contact_prev(p, (size_t)row * p.N, a1, a2);
+  uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
+  pair_upsert(p, a1, a2, first, run, was ? 0u : 1u);
+  coord_upsert(p, floor, me.x + ot.x, me.y + ot.y, (unsigned long long)run);
   if (p.log_cap) {
     // warp-aggregated append: one atomic per converged group of lanes
     cg::coalesced_group g = cg::coalesced_threads();
@@ -439,41 +518,78 @@ __device__ __forceinline__ void on_contact(const Params& p, int row, uint32_t t,
   }
 }
 
-__global__ void __launch_bounds__(256) k_pairs(Params p, int t_begin, int rows /* S */) {
-  int q0 = blockIdx.x * blockDim.x + threadIdx.x;
-  int row = blockIdx.y;
-  unsigned long long tests = 0, hits = 0;
+// One thread per located agent of one step ("me", in cell order) walks its half neighbourhood:
+// the rest of its cell, the cell to the right and the three cells of the row above.  In cell
+// order all of a block's candidates form ONE contiguous window of the sorted array, which the
+// block stages in shared memory with coalesced 16-byte loads, so the per-candidate loop runs at
+// shared-memory latency (windows beyond kWindow records are read from global memory instead).
+//
+// Stationary-run aggregation: a pair whose two agents are both provably where they were one step
+// earlier (changed == 0) was handled at the step its run started -- by the owner step's thread,
+// which added the whole run (1 + min(stay_me, stay_ot) steps, clipped to the chunk) in one
+// update -- so later steps of the run skip it without a distance evaluation.  The first step of
+// a chunk owns everything it finds.  With the contact log on, every contact-step is evaluated
+// and logged on its own (aggregate == 0).
+constexpr int kPairThreads = 256;
+constexpr int kWindow = 2560;  // records (40 KB)
+
+__global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, int rows /* S */, int aggregate) {
+  __shared__ int4 win[kWindow];
+  __shared__ int s_w1;
+  const int row = blockIdx.y;
   const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
-  int total = (int)cs[p.total_cells];
+  const int total = (int)cs[p.total_cells];
+  const int w0 = blockIdx.x * kPairThreads;
+  if (w0 >= total) return;  // whole block
+  if (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) return;  // results are void already
+  const int q0 = w0 + threadIdx.x;
+  const int4* srt = p.sorted + (size_t)row * p.N;
+  if (threadIdx.x == 0) s_w1 = w0;
+  __syncthreads();
+  int4 me = make_int4(0, 0, 0, 0);
+  int qa = 0, qa_end = 0, qb = 0, qb_end = 0, f = 0, loc = -1;
   if (q0 < total) {
-    const int4* srt = p.sorted + (size_t)row * p.N;
-    int4 me = srt[q0];
-    int f = fl_floor(me.w), loc = fl_loc(me.w);
-    const FloorDev fd = p.floors[f];
+    me = srt[q0];
+    f = fl_floor(me.w); loc = fl_loc(me.w);
+    const FloorDev& fd = p.floors[f];
     int cx = (me.x - fd.minx) / p.cell, cy = (me.y - fd.miny) / p.cell;
     int rowbase = fd.cell_base + cy * fd.ncx;
-    uint32_t t = (uint32_t)(t_begin + row);
-    // own row: rest of my cell + the cell to the right
-    int end = (int)cs[rowbase + min(cx + 1, fd.ncx - 1) + 1];
-    for (int q = q0 + 1; q < end; ++q) {
-      int4 ot = srt[q];
-      ++tests;
-      if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
-        ++hits;
-        on_contact(p, row, t, me, ot);
-      }
-    }
-    // row above: three cells
+    qa = q0 + 1;
+    qa_end = (int)cs[rowbase + min(cx + 1, fd.ncx - 1) + 1];
+    int hi = qa_end;
     if (cy + 1 < fd.ncy) {
       int rb2 = rowbase + fd.ncx;
-      int qb = (int)cs[rb2 + max(cx - 1, 0)];
-      int qe = (int)cs[rb2 + min(cx + 1, fd.ncx - 1) + 1];
-      for (int q = qb; q < qe; ++q) {
-        int4 ot = srt[q];
+      qb = (int)cs[rb2 + max(cx - 1, 0)];
+      qb_end = (int)cs[rb2 + min(cx + 1, fd.ncx - 1) + 1];
+      hi = max(hi, qb_end);
+    }
+    atomicMax(&s_w1, hi);
+  }
+  __syncthreads();
+  const int wlen = s_w1 - w0;
+  const bool staged = wlen <= kWindow;
+  if (staged) {
+    for (int i = threadIdx.x; i < wlen; i += kPairThreads) win[i] = srt[w0 + i];
+    __syncthreads();
+  }
+  unsigned long long tests = 0, hits = 0;
+  if (q0 < total) {
+    const FloorDev& fd = p.floors[f];
+    const uint32_t t = (uint32_t)(t_begin + row);
+    const bool me_still = aggregate && row > 0 && !fl_changed(me.w);
+    const int me_stay = aggregate ? fl_stay(me.w) : 0;
+    const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
+#pragma unroll 1
+    for (int rg = 0; rg < 2; ++rg) {
+      const int qs = rg ? qb : qa, qe = rg ? qb_end : qa_end;
+      for (int q = qs; q < qe; ++q) {
+        int4 ot = staged ? win[q - w0] : srt[q];
+        if (me_still && !fl_changed(ot.w)) continue;  // inside a run owned by an earlier step
         ++tests;
         if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
-          ++hits;
-          on_contact(p, row, t, me, ot);
+          uint32_t run = 1u + (uint32_t)min(me_stay, aggregate ? fl_stay(ot.w) : 0);
+          hits += run;
+          on_contact(p, row, t, me, ot, run, sub);
         }
       }
     }
@@ -487,6 +603,34 @@ __global__ void __launch_bounds__(256) k_pairs(Params p, int t_begin, int rows /
     atomicAdd(&p.ctr->pair_tests, tests);
     if (hits) atomicAdd(&p.ctr->contact_steps, hits);
   }
+}
+
+// K4b: apply the chunk's contact buffer to the tables.  One record per thread: every thread's
+// table accesses are independent, so the kernel runs at the memory system's random-access rate
+// instead of at the pace of k_pairs' longest neighbour list.  Per record: one 16-byte slot probe
+// + one 64-bit compare-and-swap on the same sector (pair table) and one 64-bit reduction
+// (coordinate histogram); for run starts that are not known continuations also two 16-byte
+// record reads for the previous-step predicate.
+constexpr int kAccBlocksPerSub = 24;
+
+__global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
+  const int sub = blockIdx.x % kSubBuffers, part = blockIdx.x / kSubBuffers;
+  const unsigned long long n = min(p.ctr->cbuf_count[sub * kCounterStride], p.cbuf_sub_cap);
+  const ContactRec* buf = p.cbuf + (unsigned long long)sub * p.cbuf_sub_cap;
+  const unsigned long long stride = (unsigned long long)kAccBlocksPerSub * blockDim.x;
+  for (unsigned long long i = (unsigned long long)part * blockDim.x + threadIdx.x; i < n; i += stride) {
+    ContactRec r = buf[i];
+    uint32_t t = r.t_run & 0xffffffu, run = (r.t_run >> 24) + 1u;
+    int row = (int)t - t_begin;  // rec row `row` holds step t-1
+    bool was = (r.bucket >> 31) ? true : contact_prev(p, (size_t)row * p.N, r.a1, r.a2);
+    uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
+    pair_upsert(p, r.a1, r.a2, first, run, was ? 0u : 1u);
+    atomicAdd(p.hist + (r.bucket & 0x7fffffffu), (unsigned long long)run);
+  }
+}
+
+__global__ void k_reset_cbuf(DevCounters* ctr) {
+  if (threadIdx.x < kSubBuffers) ctr->cbuf_count[threadIdx.x * kCounterStride] = 0ULL;
 }
 
 // --------------------------------------------------------------------------
@@ -584,9 +728,10 @@ __global__ void k_compact_pairs(const PairEntry* tab, unsigned long long cap, ci
   citam_pair r;
   r.a1 = (uint32_t)(e.key >> 32);
   r.a2 = (uint32_t)(e.key & 0xffffffffu);
-  r.first_step = 0xFFFFFFFFu - e.first_inv;
-  r.n_events = e.nev;
-  r.duration = e.dur;
+  uint32_t finv = ACC_FIRST_INV(e.acc);
+  r.first_step = finv ? 0xFFFFFFu - finv : NO_STEP;
+  r.n_events = ACC_NEV(e.acc);
+  r.duration = ACC_DUR(e.acc);
   out[base] = r;
 }
 
@@ -610,6 +755,56 @@ __global__ void k_compact_coords(const CoordEntry* tab, unsigned long long cap, 
   out[base] = r;
 }
 
+// dense histogram: count / compact the non-zero buckets of one floor
+__global__ void k_hist_count(const unsigned long long* hist, long long n, DevCounters* ctr) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long nz = (i < n && hist[i] != 0ULL) ? 1ULL : 0ULL;
+  for (int d = 16; d > 0; d >>= 1) nz += __shfl_down_sync(0xffffffffu, nz, d);
+  if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&ctr->export_cursor, nz);
+}
+
+__global__ void k_hist_compact(const unsigned long long* hist, long long n, int floor, int hist_w, int minx2, int miny2,
+                               citam_coord* out, unsigned long long out_cap, DevCounters* ctr) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long c = hist[i];
+  if (c == 0ULL) return;
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
+  base = g.shfl(base, 0) + g.thread_rank();
+  if (base >= out_cap) return;
+  citam_coord r;
+  r.floor = floor;
+  r.sx = (int32_t)(i % hist_w) + minx2;
+  r.sy = (int32_t)(i / hist_w) + miny2;
+  r.reserved = 0;
+  r.count = c;
+  out[base] = r;
+}
+
+// per-agent contact seconds = sum of the durations of the agent's pairs
+// (close_contacts_calculator.py:221-224 increments both agents once per contact-step)
+__global__ void k_agent_durations(const PairEntry* tab, unsigned long long cap, unsigned long long* agent_dur) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  PairEntry e = tab[i];
+  if (e.key == 0ULL) return;
+  unsigned long long d = ACC_DUR(e.acc);
+  atomicAdd(&agent_dur[(uint32_t)(e.key >> 32)], d);
+  atomicAdd(&agent_dur[(uint32_t)(e.key & 0xffffffffu)], d);
+}
+
+__global__ void k_rehash_pairs(Params p, const PairEntry* old_tab, unsigned long long old_cap) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= old_cap) return;
+  PairEntry e = old_tab[i];
+  if (e.key == 0ULL) return;
+  unsigned long long h = pair_slot(p, e.key);
+  if (h == ~0ULL) return;
+  p.pairs[h].acc = e.acc;  // keys are unique in the old table: no other thread touches this slot
+}
+
 // pass 1: per-agent event sums and "has a pair" flags; pass 2: reduce over agents
 __global__ void k_stats_pairs(const PairEntry* tab, unsigned long long cap, uint32_t* agent_nev,
                               uint32_t* agent_has, DevCounters* ctr) {
@@ -619,11 +814,12 @@ __global__ void k_stats_pairs(const PairEntry* tab, unsigned long long cap, uint
     PairEntry e = tab[i];
     if (e.key != 0ULL) {
       uint32_t a1 = (uint32_t)(e.key >> 32), a2 = (uint32_t)(e.key & 0xffffffffu);
-      atomicAdd(&agent_nev[a1], e.nev);
-      atomicAdd(&agent_nev[a2], e.nev);
+      uint32_t nev = ACC_NEV(e.acc);
+      atomicAdd(&agent_nev[a1], nev);
+      atomicAdd(&agent_nev[a2], nev);
       agent_has[a1] = 1;
       agent_has[a2] = 1;
-      dur = e.dur;
+      dur = ACC_DUR(e.acc);
       np = 1;
     }
   }
@@ -657,7 +853,7 @@ __global__ void k_merge_pairs(Params p, const citam_pair* in, unsigned long long
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   citam_pair r = in[i];
-  pair_upsert(p, r.a1, r.a2, r.first_step, (uint32_t)r.duration, r.n_events);
+  pair_upsert(p, r.a1, r.a2, r.first_step, r.duration, r.n_events);
 }
 
 __global__ void k_merge_coords(Params p, const citam_coord* in, unsigned long long n) {
@@ -697,23 +893,28 @@ struct citam_engine {
   bool have_itin = false;
 
   int S = 0;  // chunk capacity in steps
-  int32_t *rec_x = nullptr, *rec_y = nullptr, *rec_fl = nullptr;
-  uint32_t* rank = nullptr;
+  int4* rec = nullptr;
   uint32_t* cells = nullptr;
   int4* sorted = nullptr;
 
   PairEntry* pairs = nullptr;
   unsigned long long pair_cap = 0;
+  bool pair_auto = false;  // capacity chosen by the library: grow when half full
+  unsigned long long* hist = nullptr;  // dense coordinate histogram (all floors), NULL = hashed
+  long long hist_total = 0;
+  int32_t range_begin = -1;
   CoordEntry* coords = nullptr;
   unsigned long long coord_cap = 0;
   citam_contact* log = nullptr;
   unsigned long long log_cap = 0;
-  uint32_t* agent_dur = nullptr;
+  ContactRec* cbuf = nullptr;
+  unsigned long long cbuf_cap = 0;
+  unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
   DevCounters* ctr_d = nullptr;
 
   // Calculator.run entry: previous explicit state row
-  int32_t *prev_x = nullptr, *prev_y = nullptr, *prev_fl = nullptr;
+  int4* prev = nullptr;
   long long prev_step = LLONG_MIN;
   citam_agent_state* states_d = nullptr;
 
@@ -724,6 +925,8 @@ struct citam_engine {
   double t_ms[CITAM_N_KERNELS] = {0};
   unsigned long long t_n[CITAM_N_KERNELS] = {0};
 };
+
+constexpr long long kDenseHistMax = 1LL << 30;  // buckets (8 GiB)
 
 static unsigned long long next_pow2(unsigned long long v) {
   unsigned long long p = 1;
@@ -768,17 +971,20 @@ static Params make_params(citam_engine* e) {
   Params p{};
   p.N = e->N; p.F = e->F; p.cell = e->cell; p.total_cells = e->total_cells; p.cells_stride = e->cells_stride;
   p.D = e->D; p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
-  p.rec_x = e->rec_x; p.rec_y = e->rec_y; p.rec_fl = e->rec_fl; p.rank = e->rank; p.cells = e->cells;
-  p.sorted = e->sorted; p.pairs = e->pairs; p.pair_mask = e->pair_cap - 1; p.coords = e->coords;
-  p.coord_mask = e->coord_cap - 1; p.log = e->log; p.log_cap = e->log_cap; p.agent_dur = e->agent_dur;
+  p.rec = e->rec; p.cells = e->cells;
+  p.sorted = e->sorted; p.pairs = e->pairs; p.pair_mask = e->pair_cap - 1;
+  p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist; p.range_begin = e->range_begin;
+  p.log = e->log; p.log_cap = e->log_cap;
+  p.cbuf = (e->log_cap || !e->hist) ? nullptr : e->cbuf; p.cbuf_sub_cap = e->cbuf_cap / kSubBuffers;
   p.ctr = e->ctr_d;
   return p;
 }
 
 static void free_chunk(citam_engine* e) {
-  cudaFree(e->rec_x); cudaFree(e->rec_y); cudaFree(e->rec_fl); cudaFree(e->rank); cudaFree(e->cells);
-  cudaFree(e->sorted);
-  e->rec_x = e->rec_y = e->rec_fl = nullptr; e->rank = nullptr; e->cells = nullptr; e->sorted = nullptr;
+  cudaFree(e->rec); cudaFree(e->cells);
+  cudaFree(e->sorted); cudaFree(e->cbuf);
+  e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
+  e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
 }
 
@@ -795,32 +1001,56 @@ static int ensure_ready(citam_engine* e, int want_steps) {
     }
     e->total_cells = base;
     e->cells_stride = ((base + 1) + 3) & ~3;
+    // dense per-coordinate histogram over every floor's half-unit lattice (contact positions are
+    // midpoints of integer points); lattices beyond kDenseHistMax buckets use the hashed table.
+    // Changing a floor's lattice drops the histogram's contents (documented in the header).
+    long long tot = 0;
+    bool same = true;
+    for (auto& f : e->floors_h) {
+      int hw = f.lut ? 2 * f.W - 1 : 0, hh = f.lut ? 2 * f.H - 1 : 0;
+      if (f.hist_base != tot || f.hist_w != hw || f.hist_h != hh) same = false;
+      f.hist_base = tot; f.hist_w = hw; f.hist_h = hh;
+      tot += (long long)hw * hh;
+    }
+    if (!same || tot != e->hist_total) {
+      cudaFree(e->hist);
+      e->hist = nullptr;
+      e->hist_total = 0;
+      if (tot > 0 && tot <= kDenseHistMax && !(e->cfg.flags & CITAM_FLAG_HASHED_COORDS)) {
+        CK(cudaMalloc(&e->hist, sizeof(unsigned long long) * (size_t)tot));
+        CK(cudaMemsetAsync(e->hist, 0, sizeof(unsigned long long) * (size_t)tot, e->stream));
+        e->hist_total = tot;
+      }
+    }
     CK(cudaMemcpyAsync(e->floors_d, e->floors_h.data(), sizeof(FloorDev) * e->F, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->floors_dirty = false;
     free_chunk(e);
   }
-  if (e->S >= want_steps && e->rec_x) return CITAM_OK;
+  if (e->S >= want_steps && e->rec) return CITAM_OK;
   free_chunk(e);
   int S = want_steps;
   size_t n = (size_t)e->N;
-  CK(cudaMalloc(&e->rec_x, sizeof(int32_t) * n * (S + 1)));
-  CK(cudaMalloc(&e->rec_y, sizeof(int32_t) * n * (S + 1)));
-  CK(cudaMalloc(&e->rec_fl, sizeof(int32_t) * n * (S + 1)));
-  CK(cudaMalloc(&e->rank, sizeof(uint32_t) * n * S));
+  CK(cudaMalloc(&e->rec, sizeof(int4) * n * (S + 1)));
   CK(cudaMalloc(&e->cells, sizeof(uint32_t) * (size_t)e->cells_stride * S));
   CK(cudaMalloc(&e->sorted, sizeof(int4) * n * S));
+  // contact buffer: one record per detected contact run of a chunk (overflow falls back to
+  // inline accumulation, so the size is a performance knob, not a limit)
+  e->cbuf_cap = std::min<unsigned long long>(64ULL << 20, std::max<unsigned long long>(1ULL << 16, 2ULL * n * S));
+  e->cbuf_cap = (e->cbuf_cap + kSubBuffers - 1) / kSubBuffers * kSubBuffers;
+  CK(cudaMalloc(&e->cbuf, sizeof(ContactRec) * e->cbuf_cap));
   e->S = S;
   return CITAM_OK;
 }
 
 static int pick_chunk(citam_engine* e, int steps) {
-  if (e->cfg.steps_per_chunk > 0) return std::min(steps, e->cfg.steps_per_chunk);
-  // ~8M agent-steps per launch group, bounded by 1 GiB of histogram rows
-  long long by_agents = std::max(1LL, (8LL << 20) / std::max(1, e->N));
+  if (e->cfg.steps_per_chunk > 0) return std::min(std::min(steps, e->cfg.steps_per_chunk), kMaxChunk);
+  // ~64M agent-steps per launch group (2 GiB of per-step records), bounded by 1 GiB of histogram
+  // rows and by the 8-bit stationary-run counter
+  long long by_agents = std::max(1LL, (64LL << 20) / std::max(1, e->N));
   long long by_cells = std::max(1LL, (1LL << 28) / std::max(4, e->cells_stride));
   long long s = std::min(by_agents, by_cells);
-  s = std::min<long long>(s, 4096);
+  s = std::min<long long>(s, kMaxChunk);
   s = std::max<long long>(s, 1);
   return (int)std::min<long long>(s, steps);
 }
@@ -840,7 +1070,12 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
   {
     Timed tm(e, CITAM_K_PAIRS);
     dim3 g((e->N + 255) / 256, rows);
-    k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows);
+    k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, e->log_cap == 0 ? 1 : 0);
+  }
+  if (p.cbuf != nullptr) {
+    Timed tm(e, CITAM_K_ACCUMULATE);
+    k_accumulate<<<kSubBuffers * kAccBlocksPerSub, 256, 0, e->stream>>>(p, t_begin);
+    k_reset_cbuf<<<1, kSubBuffers, 0, e->stream>>>(e->ctr_d);
   }
   CK(cudaGetLastError());
   return CITAM_OK;
@@ -853,6 +1088,7 @@ static int check_overflow(citam_engine* e) {
   if (c.overflow & OVF_PAIR) return fail(CITAM_ERR_CAPACITY, "pair table full (%llu slots): raise pair_capacity", e->pair_cap);
   if (c.overflow & OVF_COORD) return fail(CITAM_ERR_CAPACITY, "coordinate table full (%llu slots): raise coord_capacity", e->coord_cap);
   if (c.overflow & OVF_LOG) return fail(CITAM_ERR_CAPACITY, "contact log full (%llu records): raise log_capacity", e->log_cap);
+  if (c.overflow & OVF_FIELD) return fail(CITAM_ERR_CAPACITY, "a pair exceeded 2^24-1 contact-steps or 65535 events");
   if (c.overflow & OVF_GRID) return fail(CITAM_ERR_INVALID, "an agent was given a location but lies outside its floor's lattice");
   return CITAM_OK;
 }
@@ -886,8 +1122,9 @@ int citam_create(const citam_config* cfg, citam_engine** out) {
   e->floors_h.assign(e->F, FloorDev{});
   e->lut_d.assign(e->F, nullptr);
   e->adj_d.assign(e->F, nullptr);
-  e->pair_cap = next_pow2(cfg->pair_capacity ? cfg->pair_capacity : std::max<unsigned long long>(1ULL << 16, 64ULL * e->N));
-  e->coord_cap = next_pow2(cfg->coord_capacity ? cfg->coord_capacity : std::max<unsigned long long>(1ULL << 16, 16ULL * e->N));
+  e->pair_auto = cfg->pair_capacity == 0;
+  e->pair_cap = next_pow2(cfg->pair_capacity ? cfg->pair_capacity : std::min<unsigned long long>(1ULL << 28, std::max<unsigned long long>(1ULL << 22, 256ULL * e->N)));
+  e->coord_cap = next_pow2(cfg->coord_capacity ? cfg->coord_capacity : std::min<unsigned long long>(1ULL << 27, std::max<unsigned long long>(1ULL << 20, 64ULL * e->N)));
   e->log_cap = cfg->log_capacity;
   *out = e;
   size_t n = (size_t)e->N;
@@ -895,13 +1132,11 @@ int citam_create(const citam_config* cfg, citam_engine** out) {
   CK(cudaMalloc(&e->pairs, sizeof(PairEntry) * e->pair_cap));
   CK(cudaMalloc(&e->coords, sizeof(CoordEntry) * e->coord_cap));
   if (e->log_cap) CK(cudaMalloc(&e->log, sizeof(citam_contact) * e->log_cap));
-  CK(cudaMalloc(&e->agent_dur, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->agent_dur, sizeof(unsigned long long) * n));
   CK(cudaMalloc(&e->agent_nev, sizeof(uint32_t) * n));
   CK(cudaMalloc(&e->agent_has, sizeof(uint32_t) * n));
   CK(cudaMalloc(&e->ctr_d, sizeof(DevCounters)));
-  CK(cudaMalloc(&e->prev_x, sizeof(int32_t) * n));
-  CK(cudaMalloc(&e->prev_y, sizeof(int32_t) * n));
-  CK(cudaMalloc(&e->prev_fl, sizeof(int32_t) * n));
+  CK(cudaMalloc(&e->prev, sizeof(int4) * n));
   CK(cudaMalloc(&e->states_d, sizeof(citam_agent_state) * n));
   return citam_reset(e);
 }
@@ -914,9 +1149,10 @@ void citam_destroy(citam_engine* e) {
   free_chunk(e);
   for (auto p : e->lut_d) cudaFree(p);
   for (auto p : e->adj_d) cudaFree(p);
-  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->seg_off_d); cudaFree(e->pairs); cudaFree(e->coords);
+  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->seg_off_d); cudaFree(e->pairs);
+  cudaFree(e->coords); cudaFree(e->hist);
   cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->ctr_d);
-  cudaFree(e->prev_x); cudaFree(e->prev_y); cudaFree(e->prev_fl); cudaFree(e->states_d);
+  cudaFree(e->prev); cudaFree(e->states_d);
   delete e;
 }
 
@@ -931,7 +1167,7 @@ int citam_reset(citam_engine* e) {
   CK(cudaSetDevice(e->device));
   CK(cudaMemsetAsync(e->pairs, 0, sizeof(PairEntry) * e->pair_cap, e->stream));
   CK(cudaMemsetAsync(e->coords, 0, sizeof(CoordEntry) * e->coord_cap, e->stream));
-  CK(cudaMemsetAsync(e->agent_dur, 0, sizeof(uint32_t) * (size_t)e->N, e->stream));
+  if (e->hist) CK(cudaMemsetAsync(e->hist, 0, sizeof(unsigned long long) * (size_t)e->hist_total, e->stream));
   CK(cudaMemsetAsync(e->ctr_d, 0, sizeof(DevCounters), e->stream));
   e->prev_step = LLONG_MIN;
   e->agent_steps = 0;
@@ -1049,6 +1285,37 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
   return CITAM_OK;
 }
 
+// Library-chosen pair capacity: double the table once it is half full (checked between chunks).
+static int maybe_grow_pairs(citam_engine* e) {
+  if (!e->pair_auto) return CITAM_OK;
+  DevCounters c;
+  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  while (c.pair_used * 2 > e->pair_cap && !(c.overflow & OVF_PAIR)) {
+    unsigned long long ncap = e->pair_cap * 2;
+    PairEntry* np = nullptr;
+    if (cudaMalloc(&np, sizeof(PairEntry) * ncap) != cudaSuccess) {
+      cudaGetLastError();
+      e->pair_auto = false;  // out of memory: keep the table, overflow is reported if it comes
+      return CITAM_OK;
+    }
+    CK(cudaMemsetAsync(np, 0, sizeof(PairEntry) * ncap, e->stream));
+    PairEntry* old = e->pairs;
+    unsigned long long ocap = e->pair_cap;
+    e->pairs = np; e->pair_cap = ncap;
+    CK(cudaMemsetAsync(&e->ctr_d->pair_used, 0, sizeof(unsigned long long), e->stream));
+    Params p = make_params(e);
+    {
+      Timed tm(e, CITAM_K_MISC);
+      k_rehash_pairs<<<(unsigned)((ocap + 255) / 256), 256, 0, e->stream>>>(p, old, ocap);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(old);
+  }
+  return CITAM_OK;
+}
+
 int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
   if (!e) return fail(CITAM_ERR_INVALID, "null engine");
   if (!e->have_itin) return fail(CITAM_ERR_STATE, "citam_run before citam_load_itineraries");
@@ -1060,8 +1327,9 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
   int S = pick_chunk(e, t_end - t_begin);
   rc = ensure_ready(e, S);
   if (rc) return rc;
-  Params p = make_params(e);
+  e->range_begin = t_begin;
   for (int tb = t_begin; tb < t_end; tb += S) {
+    Params p = make_params(e);
     int steps = std::min(S, t_end - tb);
     int rows = steps + 1;  // + halo row for step tb-1
     CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride * steps, e->stream));
@@ -1074,6 +1342,8 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     rc = run_sorted_stages(e, tb, steps);
     if (rc) return rc;
     e->agent_steps += (unsigned long long)steps * e->N;
+    rc = maybe_grow_pairs(e);
+    if (rc) return rc;
   }
   e->prev_step = LLONG_MIN;
   return CITAM_OK;
@@ -1089,15 +1359,14 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   int g = (e->N + 255) / 256;
   CK(cudaMemcpyAsync(e->states_d, states, sizeof(citam_agent_state) * n, cudaMemcpyHostToDevice, e->stream));
   if (e->prev_step == (long long)step - 1) {
-    CK(cudaMemcpyAsync(e->rec_x, e->prev_x, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->rec_y, e->prev_y, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->rec_fl, e->prev_fl, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->rec, e->prev, sizeof(int4) * n, cudaMemcpyDeviceToDevice, e->stream));
   } else {
-    k_fill_inactive<<<g, 256, 0, e->stream>>>(e->rec_x, e->rec_y, e->rec_fl, e->N);
+    k_fill_inactive<<<g, 256, 0, e->stream>>>(e->rec, e->N);
     e->launches++;
   }
-  k_states_to_rec<<<g, 256, 0, e->stream>>>(e->states_d, e->N, e->rec_x + n, e->rec_y + n, e->rec_fl + n);
+  k_states_to_rec<<<g, 256, 0, e->stream>>>(e->states_d, e->N, e->rec + n);
   e->launches++;
+  if (e->prev_step != (long long)step - 1) e->range_begin = step;
   CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
   Params p = make_params(e);
   {
@@ -1107,11 +1376,11 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   CK(cudaGetLastError());
   rc = run_sorted_stages(e, step, 1);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(e->prev_x, e->rec_x + n, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->prev_y, e->rec_y + n, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->prev_fl, e->rec_fl + n, 4 * n, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->prev, e->rec + n, sizeof(int4) * n, cudaMemcpyDeviceToDevice, e->stream));
   e->prev_step = step;
   e->agent_steps += e->N;
+  rc = maybe_grow_pairs(e);
+  if (rc) return rc;
   return check_overflow(e);
 }
 
@@ -1126,7 +1395,7 @@ int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out) {
     Timed tm(e, CITAM_K_MISC);
     dim3 g((e->N + 127) / 128, 1);
     k_expand_bin<<<g, 128, 0, e->stream>>>(p, step, 1, 0);
-    k_rec_to_states<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->rec_x, e->rec_y, e->rec_fl, e->N, e->states_d);
+    k_rec_to_states<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->rec, e->N, e->states_d);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, e->states_d, sizeof(citam_agent_state) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
@@ -1162,7 +1431,24 @@ int citam_pair_count(citam_engine* e, uint64_t* n) {
   return CITAM_OK;
 }
 
+static int dense_coord_count(citam_engine* e, uint64_t* n) {
+  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
+  if (e->hist_total > 0) {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_hist_count<<<(unsigned)((e->hist_total + 255) / 256), 256, 0, e->stream>>>(e->hist, e->hist_total, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, &e->ctr_d->export_cursor, sizeof v, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *n = v;
+  return CITAM_OK;
+}
+
 int citam_coord_count(citam_engine* e, uint64_t* n) {
+  if (!e || !n) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  if (e->hist) return dense_coord_count(e, n);
   citam_counters c;
   int rc = citam_get_counters(e, &c);
   if (rc) return rc;
@@ -1214,7 +1500,16 @@ int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, ui
   citam_coord* tmp = nullptr;
   CK(cudaMalloc(&tmp, sizeof(citam_coord) * have));
   CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
-  {
+  if (e->hist) {
+    Timed tm(e, CITAM_K_FINALIZE);
+    for (int f = 0; f < e->F; ++f) {
+      const FloorDev& fd = e->floors_h[f];
+      long long nb = (long long)fd.hist_w * fd.hist_h;
+      if (nb == 0) continue;
+      k_hist_compact<<<(unsigned)((nb + 255) / 256), 256, 0, e->stream>>>(e->hist + fd.hist_base, nb, f, fd.hist_w,
+                                                                          2 * fd.minx, 2 * fd.miny, tmp, have, e->ctr_d);
+    }
+  } else {
     Timed tm(e, CITAM_K_FINALIZE);
     k_compact_coords<<<(unsigned)((e->coord_cap + 255) / 256), 256, 0, e->stream>>>(e->coords, e->coord_cap, tmp, have, e->ctr_d);
   }
@@ -1230,13 +1525,25 @@ int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, ui
   return CITAM_OK;
 }
 
+static int compute_agent_durations(citam_engine* e) {
+  CK(cudaMemsetAsync(e->agent_dur, 0, sizeof(unsigned long long) * (size_t)e->N, e->stream));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_agent_durations<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, e->agent_dur);
+  }
+  CK(cudaGetLastError());
+  return CITAM_OK;
+}
+
 int citam_export_agent_durations(citam_engine* e, uint64_t* out) {
   if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->device));
-  std::vector<uint32_t> tmp((size_t)e->N);
-  CK(cudaMemcpyAsync(tmp.data(), e->agent_dur, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, e->stream));
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  rc = compute_agent_durations(e);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, e->agent_dur, sizeof(uint64_t) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i];
   return CITAM_OK;
 }
 
@@ -1297,6 +1604,10 @@ int citam_get_timings(citam_engine* e, citam_timings* out) {
 
 int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements) {
   if (!e || !ptr || !n_elements) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  int rc = compute_agent_durations(e);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(e->stream));
   *ptr = e->agent_dur;
   *n_elements = (uint64_t)e->N;
   return CITAM_OK;
@@ -1326,6 +1637,15 @@ int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n) {
   if (!e || (n && !coords)) return fail(CITAM_ERR_INVALID, "null argument");
   if (!n) return CITAM_OK;
   CK(cudaSetDevice(e->device));
+  int rc0 = ensure_ready(e, 1);
+  if (rc0) return rc0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const citam_coord& c = coords[i];
+    if (c.floor < 0 || c.floor >= e->F) return fail(CITAM_ERR_INVALID, "bad coordinate record %llu", (unsigned long long)i);
+    const FloorDev& fd = e->floors_h[c.floor];
+    if (e->hist && (c.sx < 2 * fd.minx || c.sx - 2 * fd.minx >= fd.hist_w || c.sy < 2 * fd.miny || c.sy - 2 * fd.miny >= fd.hist_h))
+      return fail(CITAM_ERR_INVALID, "coordinate record %llu lies outside floor %d", (unsigned long long)i, c.floor);
+  }
   citam_coord* tmp = nullptr;
   CK(cudaMalloc(&tmp, sizeof(citam_coord) * n));
   CK(cudaMemcpyAsync(tmp, coords, sizeof(citam_coord) * n, cudaMemcpyHostToDevice, e->stream));

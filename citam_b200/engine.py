@@ -29,6 +29,7 @@ class DeviceEngine:
         log_capacity: int = 0,
         steps_per_chunk: int = 0,
         timing: bool = False,
+        hashed_coords: bool = False,
     ):
         self.lib = L.load()
         self.n_agents = int(n_agents)
@@ -37,7 +38,8 @@ class DeviceEngine:
         cfg = L.Config(
             n_agents=self.n_agents, n_floors=self.n_floors, contact_distance=self.contact_distance,
             cell_size=cell_size, device=device, pair_capacity=pair_capacity, coord_capacity=coord_capacity,
-            log_capacity=log_capacity, steps_per_chunk=steps_per_chunk, flags=L.FLAG_TIMING if timing else 0,
+            log_capacity=log_capacity, steps_per_chunk=steps_per_chunk,
+            flags=(L.FLAG_TIMING if timing else 0) | (L.FLAG_HASHED_COORDS if hashed_coords else 0),
         )
         self._cfg = cfg
         h = C.c_void_p()
@@ -121,6 +123,14 @@ class DeviceEngine:
         if len(seg_off) != self.n_agents + 1:
             raise ValueError("seg_off must have n_agents+1 entries")
         L.check(self.lib.citam_load_itineraries(self._h, L.ptr(seg_off), L.ptr(segs), len(segs)))
+
+    def load_segments_raw(self, seg_off_ptr: int, segs_ptr: int, n_segs: int) -> None:
+        """Same as load_segments for caller-owned (e.g. pinned) host buffers given by address."""
+        L.check(self.lib.citam_load_itineraries(self._h, C.c_void_p(seg_off_ptr), C.c_void_p(segs_ptr), int(n_segs)))
+
+    def agent_durations_into(self, out_ptr: int) -> None:
+        """Per-agent contact seconds into a caller-owned uint64[n_agents] host buffer."""
+        L.check(self.lib.citam_export_agent_durations(self._h, C.c_void_p(out_ptr)))
 
     # -- stepping -------------------------------------------------------------
     def run(self, t_begin: int, t_end: int) -> None:

@@ -176,3 +176,25 @@ def dense_states(seg_off: np.ndarray, seg: np.ndarray, t: int):
         if r is not None:
             x[a], y[a], f[a] = r
     return x, y, f
+
+
+def slice_segments(seg_off: np.ndarray, seg: np.ndarray, t_lo: int, t_hi: int):
+    """Sub-store that reproduces every agent's state for steps in [t_lo, t_hi): per agent the
+    last segment starting at or before t_lo (if any) and all segments starting before t_hi.
+    Used to stream one time block's itinerary slice to a device (time-block sharding)."""
+    seg_off = np.asarray(seg_off, np.int64)
+    n = len(seg_off) - 1
+    if len(seg) == 0:
+        return seg_off.copy(), seg.copy()
+    t0 = seg["t0"].astype(np.int64)
+    c_lo = np.concatenate(([0], np.cumsum(t0 <= t_lo)))  # segments with t0 <= t_lo before index i
+    c_hi = np.concatenate(([0], np.cumsum(t0 < t_hi)))
+    n_lo = c_lo[seg_off[1:]] - c_lo[seg_off[:-1]]
+    n_hi = c_hi[seg_off[1:]] - c_hi[seg_off[:-1]]
+    first = seg_off[:-1] + np.maximum(n_lo - 1, 0)
+    last = seg_off[:-1] + n_hi  # exclusive
+    cnt = np.maximum(last - first, 0)
+    new_off = np.zeros(n + 1, np.int64)
+    np.cumsum(cnt, out=new_off[1:])
+    idx = np.repeat(first - new_off[:-1], cnt) + np.arange(int(new_off[-1]), dtype=np.int64)
+    return new_off, np.ascontiguousarray(seg[idx])

@@ -57,7 +57,9 @@ typedef struct {
   int32_t flags;            /* CITAM_FLAG_*                                            */
 } citam_config;
 
-#define CITAM_FLAG_TIMING 1 /* record CUDA events around every kernel (citam_get_timings) */
+#define CITAM_FLAG_TIMING 1        /* record CUDA events around every kernel (citam_get_timings) */
+#define CITAM_FLAG_HASHED_COORDS 2 /* keep the per-coordinate histogram in a hash table even when the
+                                      floors' lattices are small enough for the dense one          */
 
 /* One constant-velocity run of an itinerary.  Agent a's position for
  * t in [t0, next.t0) is (x0 + dx*(t-t0), y0 + dy*(t-t0)) on `floor`; before the
@@ -154,6 +156,7 @@ typedef struct {
 #define CITAM_K_LUT 4
 #define CITAM_K_FINALIZE 5
 #define CITAM_K_MISC 6
+#define CITAM_K_ACCUMULATE 7
 
 /* ---- life cycle -------------------------------------------------------- */
 int citam_abi_version(void);
@@ -207,7 +210,8 @@ int citam_get_counters(citam_engine* e, citam_counters* out);
 int citam_get_timings(citam_engine* e, citam_timings* out);
 
 /* Device views for the multi-GPU reduction (torch.distributed/NCCL all-reduce
- * straight on engine memory): per-agent contact seconds, uint32 [n_agents]. */
+ * straight on engine memory): per-agent contact seconds, uint64 [n_agents],
+ * recomputed from the pair table by this call. */
 int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements);
 /* Merge pair / coordinate records exported by another engine (other rank). */
 int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n);

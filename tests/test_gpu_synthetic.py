@@ -1,0 +1,90 @@
+"""GPU parity on synthetic facilities (BASELINE shapes at reduced size) against the C grid oracle,
+itself pinned to the reference by tests/test_oracle_golden.py.  Bit-exact integer tables."""
+import numpy as np
+import pytest
+
+from oracle_util import grid_oracle_for, tables_of
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "tiny": dict(name="tiny", over={}, T=2400),
+    "config2_small": dict(name="config2", over=dict(n_agents=3000, total_timesteps=3000), T=3000),
+    "config3_small": dict(name="config3", over=dict(n_agents=9000, total_timesteps=2400, n_floors=3, entry_window=300), T=2400),
+    "config5_small": dict(name="config5", over=dict(n_agents=3000, total_timesteps=1500), T=1500),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def synth(request):
+    from citam_b200 import synthetic as S
+
+    c = CASES[request.param]
+    fac, seg_off, segs, p = S.make_config(c["name"], seed=11, **c["over"])
+    g = grid_oracle_for(fac.geometry, 6.0, seg_off, segs)
+    g.run(0, c["T"], 8)
+    want = tables_of(g)
+    return fac, seg_off, segs, p, c["T"], want, g.contact_steps
+
+
+def _engine(fac, seg_off, segs, p, **kw):
+    from citam_b200.engine import DeviceEngine
+
+    eng = DeviceEngine(p["n_agents"], p["n_floors"], 6.0, **kw)
+    eng.load_geometry(fac.geometry)
+    eng.load_segments(seg_off, segs)
+    return eng
+
+
+def test_device_lut_equals_rectangle_rule(synth):
+    fac, seg_off, segs, p, T, want, _ = synth
+    eng = _engine(fac, seg_off, segs, p)
+    for f in range(p["n_floors"]):
+        minx, miny, lut = fac.lut_expected(f)
+        assert eng.floor_meta[f][:2] == (minx, miny)
+        assert (eng.floor_lut(f) == lut).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("chunk", [0, 37])
+def test_tables_bit_exact_vs_grid_oracle(synth, chunk):
+    fac, seg_off, segs, p, T, want, want_contacts = synth
+    eng = _engine(fac, seg_off, segs, p, steps_per_chunk=chunk)
+    eng.run(0, T)
+    got = tables_of(eng)
+    assert eng.counters()["contact_steps"] == want_contacts
+    assert got[2] == want[2]
+    assert got[0] == want[0]
+    assert got[1] == want[1]
+    eng.close()
+
+
+def test_hashed_coordinate_table_equals_dense(synth):
+    fac, seg_off, segs, p, T, want, _ = synth
+    eng = _engine(fac, seg_off, segs, p, hashed_coords=True, coord_capacity=1 << 24)
+    eng.run(0, T)
+    assert tables_of(eng)[1] == want[1]
+    eng.close()
+
+
+def test_time_blocks_in_any_order_and_merge(synth):
+    """Time-block sharding: two engines each run half of the blocks; merged tables equal a full run."""
+    fac, seg_off, segs, p, T, want, _ = synth
+    a = _engine(fac, seg_off, segs, p)
+    b = _engine(fac, seg_off, segs, p)
+    cuts = list(range(0, T, 500)) + [T]
+    for i, (t0, t1) in enumerate(zip(cuts[:-1], cuts[1:])):
+        (a if i % 2 == 0 else b).run(t0, t1)
+    a.merge(b.pairs(), b.coords())
+    assert tables_of(a) == want
+    a.close()
+    b.close()
+
+
+def test_auto_capacity_grows(synth):
+    """Library-chosen pair capacity starts small and doubles when half full."""
+    fac, seg_off, segs, p, T, want, _ = synth
+    eng = _engine(fac, seg_off, segs, p, steps_per_chunk=100)
+    eng.run(0, T)
+    assert tables_of(eng)[0] == want[0]
+    eng.close()
