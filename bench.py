@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="engine steps_per_chunk (0 = auto)")
+    ap.add_argument("--pair-cap-log2", type=int, default=0, help="pair table slots = 2^k (0 = sized for the workload)")
     return ap.parse_args()
 
 
@@ -254,6 +255,8 @@ def run_b200(args):
     K, W = args.steps, max(3, args.warmup)
 
     pair_cap = int(min(1 << 31, max(1 << 22, 2048 * N)))
+    if args.pair_cap_log2:
+        pair_cap = 1 << args.pair_cap_log2
     coord_cap = int(min(1 << 27, max(1 << 22, 64 * N)))
     eng = DeviceEngine(N, p["n_floors"], D, device=local, pair_capacity=pair_cap, coord_capacity=coord_cap,
                        steps_per_chunk=args.chunk, timing=True)
@@ -299,6 +302,9 @@ def run_b200(args):
     launches = c1["kernel_launches"] - c0["kernel_launches"]
 
     log("timed region done: %.1f ms, contacts %d, counters %s" % (ms, contacts, c1))
+    if c1["overflow"]:
+        raise SystemExit("bench.py: a device table overflowed (flags %d); the timed numbers are void - raise the capacities"
+                         % c1["overflow"])
     # ---- roofline of the dominant kernel -----------------------------------------------------
     peak, peak_src = peaks()
     kern = {}

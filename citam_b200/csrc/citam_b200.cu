@@ -116,6 +116,7 @@ struct DevCounters {
   unsigned long long stats[6];
   unsigned long long pad[3];
   unsigned long long cbuf_count[kSubBuffers * kCounterStride];
+  unsigned long long pair_used_sub[kSubBuffers * kCounterStride];  // spread: inserts are frequent
 };
 
 struct Params {
@@ -140,6 +141,8 @@ struct Params {
   unsigned long long log_cap;
   ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
   unsigned long long cbuf_sub_cap;
+  uint32_t* chg_list;   // [S][N] located agents whose state may differ from the step before
+  uint32_t* chg_count;  // [S] x 32 (one counter per 128 bytes); NULL = lists not kept
   DevCounters* ctr;
 };
 
@@ -244,6 +247,10 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
     if (do_bin && row >= 1 && loc >= 0) {
       int key = cell_of(p.floors[f], p.cell, x, y);
       rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
+      if (changed && p.chg_count != nullptr) {
+        uint32_t ix = atomicAdd(&p.chg_count[(row - 1) * 32], 1u);
+        p.chg_list[(size_t)(row - 1) * p.N + ix] = (uint32_t)a;
+      }
     }
     p.rec[o] = make_int4(x, y, pack_fl(f, loc, changed, stay), (int)rk);
   }
@@ -394,16 +401,33 @@ __device__ __forceinline__ bool within(int dx, int dy, double D) {
 // (CITAM_ERR_CAPACITY) instead of degrading into a scan of the whole table.
 constexpr int kMaxProbes = 256;
 
-// Find or insert the pair's slot.  Returns the slot index, or ~0 when the table is full.
-__device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigned long long key) {
+__device__ __forceinline__ ulonglong2 load_entry(const PairEntry* e) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(e));
+  return v;
+}
+
+// New pairs are counted per sub-counter and per converged group of lanes: with transient
+// contacts most updates insert, and a single counter would serialise them at the L2.
+__device__ __forceinline__ void count_insert(const Params& p) {
+  cg::coalesced_group g = cg::coalesced_threads();
+  if (g.thread_rank() == 0)
+    atomicAdd(&p.ctr->pair_used_sub[((blockIdx.x + blockIdx.y) & (kSubBuffers - 1)) * kCounterStride],
+              (unsigned long long)g.size());
+}
+
+// Find or insert the pair's slot.  Returns the slot index (or ~0 when the table is full) and the
+// accumulator word last seen there, fetched with the key in one 16-byte load.
+__device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigned long long key,
+                                                        unsigned long long* acc_seen) {
   unsigned long long h = mix64(key) & p.pair_mask;
   for (int probe = 0; probe < kMaxProbes; ++probe) {
-    unsigned long long k = *(volatile unsigned long long*)&p.pairs[h].key;
-    if (k == key) return h;
-    if (k == 0ULL) {
+    ulonglong2 e = load_entry(&p.pairs[h]);
+    if (e.x == key) { *acc_seen = e.y; return h; }
+    if (e.x == 0ULL) {
       unsigned long long old = atomicCAS(&p.pairs[h].key, 0ULL, key);
-      if (old == 0ULL) { atomicAdd(&p.ctr->pair_used, 1ULL); return h; }
-      if (old == key) return h;
+      if (old == 0ULL) { count_insert(p); *acc_seen = 0ULL; return h; }
+      if (old == key) { *acc_seen = *(volatile unsigned long long*)&p.pairs[h].acc; return h; }
     }
     h = (h + 1) & p.pair_mask;
   }
@@ -411,24 +435,18 @@ __device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigne
   return ~0ULL;
 }
 
+__device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
+                                           unsigned long long add_dur, unsigned long long add_nev);
 // add_dur contact-steps and add_nev events; `first` (a step, or NO_STEP) lowers the pair's
 // first-contact step.  The first contact of a pair is always an event start, so callers pass a
 // step only for event starts and for the first step of a run range.
 __device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32_t a2, uint32_t first,
                                             unsigned long long add_dur, unsigned long long add_nev) {
   unsigned long long key = ((unsigned long long)a1 << 32) | a2;
-  unsigned long long h = pair_slot(p, key);
+  unsigned long long old;
+  unsigned long long h = pair_slot(p, key, &old);
   if (h == ~0ULL) return;
-  unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
-  unsigned long long old = *(volatile unsigned long long*)&p.pairs[h].acc;
-  for (;;) {
-    unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
-    if (d > 0xffffffULL || n > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
-    unsigned long long f = max((unsigned long long)ACC_FIRST_INV(old), finv);
-    unsigned long long seen = atomicCAS(&p.pairs[h].acc, old, d | (n << 24) | (f << 40));
-    if (seen == old) return;
-    old = seen;
-  }
+  pair_apply(p, h, old, first, add_dur, add_nev);
 }
 
 __device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx, int sy, unsigned long long add) {
@@ -460,8 +478,7 @@ __device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx,
 // Was the pair in contact at the previous step?  Full predicate on the halo/previous row
 // (contacts.py:131-133: an event continues iff last.start_step + last.duration == step).
 // One 16-byte record per agent: two sector reads.
-__device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
-  int4 r1 = p.rec[prow_off + a1], r2 = p.rec[prow_off + a2];
+__device__ __forceinline__ bool contact_eval(const Params& p, const int4& r1, const int4& r2) {
   int fl1 = fl_floor(r1.z), fl2 = fl_floor(r2.z);
   int l1 = fl_loc(r1.z), l2 = fl_loc(r2.z);
   if (fl1 < 0 || fl1 != fl2 || l1 < 0 || l2 < 0) return false;
@@ -470,6 +487,23 @@ __device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, u
   if (dx > lim || dx < -lim || dy > lim || dy < -lim) return false;
   if (!within((int)dx, (int)dy, p.D)) return false;
   return loc_rule(p.floors[fl1], l1, l2);
+}
+__device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
+  return contact_eval(p, p.rec[prow_off + a1], p.rec[prow_off + a2]);
+}
+
+// pair_upsert split in two so that a caller can put independent loads between probe and update
+__device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
+                                           unsigned long long add_dur, unsigned long long add_nev) {
+  unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
+  for (;;) {
+    unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
+    if (d > 0xffffffULL || n > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
+    unsigned long long f = max((unsigned long long)ACC_FIRST_INV(old), finv);
+    unsigned long long seen = atomicCAS(&p.pairs[h].acc, old, d | (n << 24) | (f << 40));
+    if (seen == old) return;
+    old = seen;
+  }
 }
 
 // A contact found at step t that lasts `run` steps (both agents provably stay put for run-1
@@ -605,6 +639,56 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
   }
 }
 
+// Steps after the first of a chunk: only agents whose state may have changed can start, end or
+// move a contact (everything else is inside a run that an earlier step already added), so one
+// thread per changed agent (taken from the compact per-step list k_expand_bin wrote) tests its
+// full 3x3 neighbourhood: three contiguous ranges of the sorted array.  A pair of two changed
+// agents is owned by the lower id.
+__global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, int rows /* S */) {
+  const int row = blockIdx.y + 1;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = p.chg_count[row * 32];
+  if (blockIdx.x * blockDim.x >= n) return;
+  if (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) return;
+  const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
+  const int4* srt = p.sorted + (size_t)row * p.N;
+  const uint32_t t = (uint32_t)(t_begin + row);
+  const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
+  unsigned long long tests = 0, hits = 0;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int a = (int)p.chg_list[(size_t)row * p.N + idx];
+    const int4 r = p.rec[(size_t)(row + 1) * p.N + a];
+    const int4 me = make_int4(r.x, r.y, a, r.z);
+    const int f = fl_floor(r.z), loc = fl_loc(r.z), me_stay = fl_stay(r.z);
+    const FloorDev& fd = p.floors[f];
+    const int cx = (r.x - fd.minx) / p.cell, cy = (r.y - fd.miny) / p.cell;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, fd.ncy - 1); ++yy) {
+      const int rb = fd.cell_base + yy * fd.ncx;
+      const int qs = (int)cs[rb + x0], qe = (int)cs[rb + x1 + 1];
+      for (int q = qs; q < qe; ++q) {
+        const int4 ot = srt[q];
+        if (ot.z == a) continue;
+        if (fl_changed(ot.w) && ot.z < a) continue;  // that agent's warp owns the pair
+        ++tests;
+        if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
+          uint32_t run = 1u + (uint32_t)min(me_stay, fl_stay(ot.w));
+          hits += run;
+          on_contact(p, row, t, me, ot, run, sub);
+        }
+      }
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    tests += __shfl_down_sync(0xffffffffu, tests, d);
+    hits += __shfl_down_sync(0xffffffffu, hits, d);
+  }
+  if (lane == 0 && (tests | hits)) {
+    atomicAdd(&p.ctr->pair_tests, tests);
+    if (hits) atomicAdd(&p.ctr->contact_steps, hits);
+  }
+}
+
 // K4b: apply the chunk's contact buffer to the tables.  One record per thread: every thread's
 // table accesses are independent, so the kernel runs at the memory system's random-access rate
 // instead of at the pace of k_pairs' longest neighbour list.  Per record: one 16-byte slot probe
@@ -622,10 +706,21 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
     ContactRec r = buf[i];
     uint32_t t = r.t_run & 0xffffffu, run = (r.t_run >> 24) + 1u;
     int row = (int)t - t_begin;  // rec row `row` holds step t-1
-    bool was = (r.bucket >> 31) ? true : contact_prev(p, (size_t)row * p.N, r.a1, r.a2);
-    uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
-    pair_upsert(p, r.a1, r.a2, first, run, was ? 0u : 1u);
+    const bool known = r.bucket >> 31;
+    // issue the previous-step record reads, the histogram reduction and the table probe
+    // back to back; none depends on another
+    int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
+    if (!known) {
+      r1 = p.rec[(size_t)row * p.N + r.a1];
+      r2 = p.rec[(size_t)row * p.N + r.a2];
+    }
     atomicAdd(p.hist + (r.bucket & 0x7fffffffu), (unsigned long long)run);
+    unsigned long long acc;
+    unsigned long long h = pair_slot(p, ((unsigned long long)r.a1 << 32) | r.a2, &acc);
+    if (h == ~0ULL) continue;
+    bool was = known ? true : contact_eval(p, r1, r2);
+    uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
+    pair_apply(p, h, acc, first, run, was ? 0u : 1u);
   }
 }
 
@@ -800,7 +895,8 @@ __global__ void k_rehash_pairs(Params p, const PairEntry* old_tab, unsigned long
   if (i >= old_cap) return;
   PairEntry e = old_tab[i];
   if (e.key == 0ULL) return;
-  unsigned long long h = pair_slot(p, e.key);
+  unsigned long long seen;
+  unsigned long long h = pair_slot(p, e.key, &seen);
   if (h == ~0ULL) return;
   p.pairs[h].acc = e.acc;  // keys are unique in the old table: no other thread touches this slot
 }
@@ -888,6 +984,8 @@ struct citam_engine {
   int total_cells = 0, cells_stride = 4;
 
   int4* segs_d = nullptr;
+  citam_segment* raw_d = nullptr;  // staging copy of the caller's records
+  int64_t segs_cap = 0;
   long long* seg_off_d = nullptr;
   long long n_segs = 0;
   bool have_itin = false;
@@ -909,6 +1007,7 @@ struct citam_engine {
   unsigned long long log_cap = 0;
   ContactRec* cbuf = nullptr;
   unsigned long long cbuf_cap = 0;
+  uint32_t *chg_list = nullptr, *chg_count = nullptr;
   unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
   DevCounters* ctr_d = nullptr;
@@ -967,6 +1066,12 @@ static void drain_timings(citam_engine* e) {
   e->evs.clear();
 }
 
+static unsigned long long pairs_used(const DevCounters& c) {
+  unsigned long long n = c.pair_used;
+  for (int i = 0; i < kSubBuffers; ++i) n += c.pair_used_sub[i * kCounterStride];
+  return n;
+}
+
 static Params make_params(citam_engine* e) {
   Params p{};
   p.N = e->N; p.F = e->F; p.cell = e->cell; p.total_cells = e->total_cells; p.cells_stride = e->cells_stride;
@@ -976,13 +1081,16 @@ static Params make_params(citam_engine* e) {
   p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist; p.range_begin = e->range_begin;
   p.log = e->log; p.log_cap = e->log_cap;
   p.cbuf = (e->log_cap || !e->hist) ? nullptr : e->cbuf; p.cbuf_sub_cap = e->cbuf_cap / kSubBuffers;
+  const bool agg = e->log_cap == 0;  // run aggregation (off when every contact-step is logged)
+  p.chg_list = agg ? e->chg_list : nullptr; p.chg_count = agg ? e->chg_count : nullptr;
   p.ctr = e->ctr_d;
   return p;
 }
 
 static void free_chunk(citam_engine* e) {
   cudaFree(e->rec); cudaFree(e->cells);
-  cudaFree(e->sorted); cudaFree(e->cbuf);
+  cudaFree(e->sorted); cudaFree(e->cbuf); cudaFree(e->chg_list); cudaFree(e->chg_count);
+  e->chg_list = e->chg_count = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -1036,9 +1144,11 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->sorted, sizeof(int4) * n * S));
   // contact buffer: one record per detected contact run of a chunk (overflow falls back to
   // inline accumulation, so the size is a performance knob, not a limit)
-  e->cbuf_cap = std::min<unsigned long long>(64ULL << 20, std::max<unsigned long long>(1ULL << 16, 2ULL * n * S));
+  e->cbuf_cap = std::min<unsigned long long>(256ULL << 20, std::max<unsigned long long>(1ULL << 16, 4ULL * n * S));
   e->cbuf_cap = (e->cbuf_cap + kSubBuffers - 1) / kSubBuffers * kSubBuffers;
   CK(cudaMalloc(&e->cbuf, sizeof(ContactRec) * e->cbuf_cap));
+  CK(cudaMalloc(&e->chg_list, sizeof(uint32_t) * n * S));
+  CK(cudaMalloc(&e->chg_count, sizeof(uint32_t) * 32 * S));
   e->S = S;
   return CITAM_OK;
 }
@@ -1069,8 +1179,14 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
   }
   {
     Timed tm(e, CITAM_K_PAIRS);
-    dim3 g((e->N + 255) / 256, rows);
-    k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, e->log_cap == 0 ? 1 : 0);
+    const bool agg = p.chg_count != nullptr;
+    // first step of the chunk (or every step when the log is on): all located agents
+    dim3 g((e->N + 255) / 256, agg ? 1 : rows);
+    k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0);
+    if (agg && rows > 1) {
+      dim3 g2((unsigned)std::min(2048, std::max(1, (e->N + 255) / 256)), rows - 1);
+      k_pairs_changed<<<g2, 256, 0, e->stream>>>(p, t_begin, rows);
+    }
   }
   if (p.cbuf != nullptr) {
     Timed tm(e, CITAM_K_ACCUMULATE);
@@ -1149,7 +1265,7 @@ void citam_destroy(citam_engine* e) {
   free_chunk(e);
   for (auto p : e->lut_d) cudaFree(p);
   for (auto p : e->adj_d) cudaFree(p);
-  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->seg_off_d); cudaFree(e->pairs);
+  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->pairs);
   cudaFree(e->coords); cudaFree(e->hist);
   cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->ctr_d);
   cudaFree(e->prev); cudaFree(e->states_d);
@@ -1265,12 +1381,18 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
   if (!e || !seg_off || (n_segs > 0 && !segs)) return fail(CITAM_ERR_INVALID, "null argument");
   if (seg_off[0] != 0 || seg_off[e->N] != n_segs) return fail(CITAM_ERR_INVALID, "seg_off must run from 0 to n_segs");
   CK(cudaSetDevice(e->device));
-  cudaFree(e->segs_d); cudaFree(e->seg_off_d);
-  e->segs_d = nullptr; e->seg_off_d = nullptr; e->have_itin = false;
-  citam_segment* raw = nullptr;
-  CK(cudaMalloc(&e->segs_d, sizeof(int4) * std::max<int64_t>(1, n_segs)));
-  CK(cudaMalloc(&e->seg_off_d, sizeof(long long) * ((size_t)e->N + 1)));
-  CK(cudaMalloc(&raw, sizeof(citam_segment) * std::max<int64_t>(1, n_segs)));
+  e->have_itin = false;
+  // buffers are kept between calls (time-block streaming reloads a slice per block)
+  if (n_segs > e->segs_cap || !e->segs_d) {
+    cudaFree(e->segs_d); cudaFree(e->raw_d);
+    e->segs_d = nullptr; e->raw_d = nullptr; e->segs_cap = 0;
+    int64_t cap = std::max<int64_t>(1024, n_segs + n_segs / 4);
+    CK(cudaMalloc(&e->segs_d, sizeof(int4) * cap));
+    CK(cudaMalloc(&e->raw_d, sizeof(citam_segment) * cap));
+    e->segs_cap = cap;
+  }
+  if (!e->seg_off_d) CK(cudaMalloc(&e->seg_off_d, sizeof(long long) * ((size_t)e->N + 1)));
+  citam_segment* raw = e->raw_d;
   CK(cudaMemcpyAsync(e->seg_off_d, seg_off, sizeof(long long) * ((size_t)e->N + 1), cudaMemcpyHostToDevice, e->stream));
   if (n_segs) {
     CK(cudaMemcpyAsync(raw, segs, sizeof(citam_segment) * n_segs, cudaMemcpyHostToDevice, e->stream));
@@ -1278,8 +1400,7 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
     k_repack_segments<<<(unsigned)((n_segs + 255) / 256), 256, 0, e->stream>>>(raw, n_segs, e->segs_d);
   }
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(e->stream));
-  cudaFree(raw);
+  CK(cudaStreamSynchronize(e->stream));  // the caller's host buffers are free to change again
   e->n_segs = n_segs;
   e->have_itin = true;
   return CITAM_OK;
@@ -1291,7 +1412,7 @@ static int maybe_grow_pairs(citam_engine* e) {
   DevCounters c;
   CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  while (c.pair_used * 2 > e->pair_cap && !(c.overflow & OVF_PAIR)) {
+  while (pairs_used(c) * 2 > e->pair_cap && !(c.overflow & OVF_PAIR)) {
     unsigned long long ncap = e->pair_cap * 2;
     PairEntry* np = nullptr;
     if (cudaMalloc(&np, sizeof(PairEntry) * ncap) != cudaSuccess) {
@@ -1304,6 +1425,7 @@ static int maybe_grow_pairs(citam_engine* e) {
     unsigned long long ocap = e->pair_cap;
     e->pairs = np; e->pair_cap = ncap;
     CK(cudaMemsetAsync(&e->ctr_d->pair_used, 0, sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->ctr_d->pair_used_sub, 0, sizeof(c.pair_used_sub), e->stream));
     Params p = make_params(e);
     {
       Timed tm(e, CITAM_K_MISC);
@@ -1333,6 +1455,7 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     int steps = std::min(S, t_end - tb);
     int rows = steps + 1;  // + halo row for step tb-1
     CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride * steps, e->stream));
+    CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
     {
       Timed tm(e, CITAM_K_EXPAND_BIN);
       dim3 g((e->N + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
@@ -1414,7 +1537,7 @@ int citam_get_counters(citam_engine* e, citam_counters* out) {
   out->pair_tests = c.pair_tests;
   out->contact_steps = c.contact_steps;
   out->kernel_launches = e->launches;
-  out->pair_slots_used = c.pair_used;
+  out->pair_slots_used = pairs_used(c);
   out->coord_slots_used = c.coord_used;
   out->log_records = std::min<unsigned long long>(c.log_count, e->log_cap);
   out->overflow = c.overflow;
