@@ -92,9 +92,9 @@ CONTACT = np.dtype([("step", "<u4"), ("a1", "<u4"), ("a2", "<u4")])
 EXPORTS = [
     "citam_abi_version", "citam_last_error", "citam_create", "citam_destroy", "citam_set_stream",
     "citam_build_floor_lut", "citam_set_floor_lut", "citam_get_floor_lut", "citam_set_floor_adjacency",
-    "citam_load_itineraries", "citam_run", "citam_step_states", "citam_states_at", "citam_reset",
+    "citam_load_itineraries", "citam_run", "citam_step_states", "citam_states_at", "citam_states_range", "citam_reset",
     "citam_pair_count", "citam_export_pairs", "citam_export_agent_durations", "citam_coord_count",
-    "citam_export_coords", "citam_export_contact_log", "citam_statistics", "citam_get_counters",
+    "citam_export_coords", "citam_export_contact_log", "citam_clear_contact_log", "citam_statistics", "citam_get_counters",
     "citam_get_timings", "citam_agent_durations_device", "citam_merge_pairs", "citam_merge_coords",
 ]
 
@@ -129,6 +129,7 @@ def load() -> C.CDLL:
         "citam_run": (C.c_int, [vp, i32, i32]),
         "citam_step_states": (C.c_int, [vp, i32, vp]),
         "citam_states_at": (C.c_int, [vp, i32, vp]),
+        "citam_states_range": (C.c_int, [vp, i32, i32, vp]),
         "citam_reset": (C.c_int, [vp]),
         "citam_pair_count": (C.c_int, [vp, pu64]),
         "citam_export_pairs": (C.c_int, [vp, vp, u64, pu64]),
@@ -136,6 +137,7 @@ def load() -> C.CDLL:
         "citam_coord_count": (C.c_int, [vp, pu64]),
         "citam_export_coords": (C.c_int, [vp, vp, u64, pu64]),
         "citam_export_contact_log": (C.c_int, [vp, vp, u64, pu64]),
+        "citam_clear_contact_log": (C.c_int, [vp]),
         "citam_statistics": (C.c_int, [vp, C.POINTER(Stats)]),
         "citam_get_counters": (C.c_int, [vp, C.POINTER(Counters)]),
         "citam_get_timings": (C.c_int, [vp, C.POINTER(Timings)]),

@@ -289,8 +289,8 @@ __global__ void k_states_to_rec(const citam_agent_state* st, int N, int4* rec) {
   rec[a] = make_int4(s.x, s.y, pack_fl(f, l), 0);
 }
 
-__global__ void k_rec_to_states(const int4* rec, int N, citam_agent_state* st) {
-  int a = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_rec_to_states(const int4* rec, long long N, citam_agent_state* st) {
+  long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= N) return;
   int4 r = rec[a];
   citam_agent_state s;
@@ -1527,6 +1527,37 @@ int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out) {
   return CITAM_OK;
 }
 
+int citam_states_range(citam_engine* e, int32_t t_begin, int32_t t_end, citam_agent_state* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  if (!e->have_itin) return fail(CITAM_ERR_STATE, "no itineraries loaded");
+  if (t_begin < 0 || t_end < t_begin) return fail(CITAM_ERR_INVALID, "bad step range");
+  if (t_end == t_begin) return CITAM_OK;
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_ready(e, 1);
+  if (rc) return rc;
+  const int rows_max = std::max(1, std::min(e->S + 1, t_end - t_begin));
+  size_t n = (size_t)e->N;
+  citam_agent_state* tmp = nullptr;
+  CK(cudaMalloc(&tmp, sizeof(citam_agent_state) * n * rows_max));
+  Params p = make_params(e);
+  for (int tb = t_begin; tb < t_end; tb += rows_max) {
+    int rows = std::min(rows_max, t_end - tb);
+    {
+      Timed tm(e, CITAM_K_MISC);
+      dim3 g((e->N + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
+      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb, rows, 0);
+      size_t tot = n * rows;
+      k_rec_to_states<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->rec, (long long)tot, tmp);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + (size_t)(tb - t_begin) * n, tmp, sizeof(citam_agent_state) * n * rows, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  cudaFree(tmp);
+  e->prev_step = LLONG_MIN;
+  return CITAM_OK;
+}
+
 int citam_get_counters(citam_engine* e, citam_counters* out) {
   if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->device));
@@ -1688,6 +1719,13 @@ int citam_export_contact_log(citam_engine* e, citam_contact* out, uint64_t capac
     if (a.a1 != b.a1) return a.a1 < b.a1;
     return a.a2 < b.a2;
   });
+  return CITAM_OK;
+}
+
+int citam_clear_contact_log(citam_engine* e) {
+  if (!e) return fail(CITAM_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(&e->ctr_d->log_count, 0, sizeof(unsigned long long), e->stream));
   return CITAM_OK;
 }
 

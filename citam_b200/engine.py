@@ -147,6 +147,13 @@ class DeviceEngine:
         L.check(self.lib.citam_states_at(self._h, int(step), L.ptr(out)))
         return out
 
+    def states_range(self, t_begin: int, t_end: int) -> np.ndarray:
+        """Agent states for every step of [t_begin, t_end): array [t_end - t_begin, n_agents]."""
+        out = np.empty((max(0, t_end - t_begin), self.n_agents), L.AGENT_STATE)
+        if out.size:
+            L.check(self.lib.citam_states_range(self._h, int(t_begin), int(t_end), L.ptr(out)))
+        return out
+
     def reset(self) -> None:
         L.check(self.lib.citam_reset(self._h))
 
@@ -176,6 +183,13 @@ class DeviceEngine:
         n = C.c_uint64()
         L.check(self.lib.citam_export_contact_log(self._h, L.ptr(out), len(out), C.byref(n)))
         return out[: n.value]
+
+    def clear_contact_log(self) -> None:
+        L.check(self.lib.citam_clear_contact_log(self._h))
+
+    @property
+    def log_enabled(self) -> bool:
+        return self._cfg.log_capacity > 0
 
     def statistics_sums(self) -> Dict[str, int]:
         s = L.Stats()

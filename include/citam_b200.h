@@ -196,6 +196,8 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
 /* Agent states at one step from the loaded itineraries (trajectory writer,
  * simulation.py:312-334). */
 int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out /* [n_agents] */);
+/* Same for every step of [t_begin, t_end): out[(t - t_begin) * n_agents + a]. */
+int citam_states_range(citam_engine* e, int32_t t_begin, int32_t t_end, citam_agent_state* out);
 int citam_reset(citam_engine* e); /* clear all accumulators, keep facility + itineraries */
 
 /* ---- results: replaces ContactEvents / extract_* ------------------------ */
@@ -205,6 +207,7 @@ int citam_export_agent_durations(citam_engine* e, uint64_t* out /* [n_agents] */
 int citam_coord_count(citam_engine* e, uint64_t* n);
 int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, uint64_t* n);
 int citam_export_contact_log(citam_engine* e, citam_contact* out, uint64_t capacity, uint64_t* n);
+int citam_clear_contact_log(citam_engine* e); /* drop exported records (block-wise full-fidelity writers) */
 int citam_statistics(citam_engine* e, citam_stats* out);
 int citam_get_counters(citam_engine* e, citam_counters* out);
 int citam_get_timings(citam_engine* e, citam_timings* out);
