@@ -367,6 +367,25 @@ def run_b200(args):
         eng.load_segments(seg_off, segs)
 
     log("e2e done")
+    # ---- end-of-run reduction (multi-GPU only; outside the per-step timing) ---------------------------
+    final_reduce_ms = None
+    if dist is not None:
+        ptr, n_el = eng.agent_durations_device()
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n_el,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+        tdur = torch.as_tensor(_Holder(), device="cuda")
+        sums = eng.statistics_sums()
+        tsum = torch.tensor([sums["total_duration"], sums["n_pairs"]], dtype=torch.int64, device="cuda")
+        barrier()
+        ev0.record()
+        dist.all_reduce(tdur)
+        dist.all_reduce(tsum)
+        ev1.record()
+        torch.cuda.synchronize()
+        final_reduce_ms = ev0.elapsed_time(ev1)
+
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -387,7 +406,8 @@ def run_b200(args):
             "dtype": "i32 positions, f64 distance predicate", "data": "synthetic",
             "config": workload_config(args, p, block),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
-            "contact_steps_per_step": contacts / K, "pair_tests_per_s": pair_tests / (ms * 1e-3),
+            "contact_steps_per_step": contacts / K, "contacts_per_agent_step": contacts / units_rank,
+            "pair_tests_per_s": pair_tests / (ms * 1e-3), "final_reduce_ms": final_reduce_ms,
         }
         print(json.dumps(line), flush=True)
     eng.close()
