@@ -71,6 +71,26 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), or None."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_top_kernels.csv")
+    names = {"accumulate": "k_accumulate", "pairs": "k_pairs_changed", "expand_bin": "k_expand_bin"}
+    if not os.path.isfile(path) or kernel not in names:
+        return None
+    rows = list(csv.reader(open(path)))
+    if not rows or names[kernel] not in rows[0]:
+        return None
+    col = rows[0].index(names[kernel])
+    tot = 0.0
+    for r in rows[1:]:
+        if r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(r[1], 1.0)
+            tot += float(r[col]) * scale
+    return tot or None
+
+
 def block_starts(T: int, block: int, count: int, rank: int, world: int, offset: int = 0):
     """`count` block start times for this rank, spread evenly over [0, T - block]."""
     total = count * world
@@ -321,7 +341,8 @@ def run_b200(args):
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
         roof = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": profiled_traffic(dom), "traffic_source": "profiles/r1_ncu_full_top_kernels.csv (one launch, 64 steps x 1e6 agents)",
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
             "kernel_share_of_step": kern[dom]["ms"] / ms,
             "kernels_ms": {k: round(v["ms"], 3) for k, v in kern.items()},

@@ -99,7 +99,7 @@ struct __align__(16) CoordEntry {
 struct __align__(16) ContactRec {
   uint32_t a1, a2;   // a1 < a2
   uint32_t t_run;    // step (24 bits) | (run - 1) << 24
-  uint32_t bucket;   // dense-histogram bucket (30 bits) | bit 31: in contact at t-1 is already known
+  uint32_t bucket;   // dense-histogram bucket (30 bits) | bit 31: in contact at t-1 | bit 30: evaluate that at accumulation
 };
 
 constexpr int kSubBuffers = 64;    // the contact buffer is split so that appends do not all hit one counter
@@ -125,6 +125,7 @@ struct Params {
   int32_t total_cells;
   int32_t cells_stride;  // uint32 per step row of the histogram (>= total_cells+1, multiple of 4)
   double D;
+  long long s_max;  // largest integer s with sqrt_rn((double)s) < D  (-1: none)
   const FloorDev* floors;
   const int4* segs;  // {t0 | floor<<24, x0, y0, dx&0xffff | dy<<16}
   const long long* seg_off;
@@ -137,6 +138,7 @@ struct Params {
   unsigned long long coord_mask;
   unsigned long long* hist;  // dense histogram, NULL = use the hash
   int32_t range_begin;       // first step of the current citam_run range
+  int32_t chunk_begin;       // first step of the chunk being processed
   citam_contact* log;
   unsigned long long log_cap;
   ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
@@ -196,9 +198,8 @@ __device__ __forceinline__ int cell_of(const FloorDev& fd, int cell, int x, int 
 // advances monotonically, the location table is touched only when the position changes, and
 // every 16-byte record store is coalesced over the 32 agents of a warp.
 // --------------------------------------------------------------------------
-constexpr int kRowsPerThread = 16;
 
-__global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int rows, int do_bin) {
+__global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int rows, int do_bin, int kRowsPerThread) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= p.N) return;
   int r0 = blockIdx.y * kRowsPerThread;
@@ -389,12 +390,18 @@ __device__ __forceinline__ bool loc_rule_ordered(const FloorDev& fd, int ida, in
   return ida < idb ? loc_rule(fd, la, lb) : loc_rule(fd, lb, la);
 }
 
-__device__ __forceinline__ bool within(int dx, int dy, double D) {
-  // scipy pdist (euclidean) on integer coordinates: sqrt(dx*dx+dy*dy) in float64, then the
-  // strict `< contact_distance` of np.argwhere (close_contacts_calculator.py:169-171).
-  // dx, dy are exact integers, so the squared sum is exact and one IEEE sqrt reproduces it.
+// scipy pdist (euclidean) on integer coordinates: sqrt(dx*dx+dy*dy) in float64, then the strict
+// `< contact_distance` of np.argwhere (close_contacts_calculator.py:169-171).  dx, dy are exact
+// integers, so s = dx^2+dy^2 is exact, and s -> sqrt_rn((double)s) is monotone: the predicate
+// holds exactly for s <= s_max, where the host found s_max with the same IEEE operations
+// (find_s_max; checked against the float64 form by within_f64 in the tests' LUT/step paths).
+__device__ __forceinline__ bool within_f64(int dx, int dy, double D) {
   long long s = (long long)dx * dx + (long long)dy * dy;
   return __dsqrt_rn((double)s) < D;
+}
+__device__ __forceinline__ bool within(int dx, int dy, const Params& p) {
+  long long s = (long long)dx * dx + (long long)dy * dy;
+  return s <= p.s_max;
 }
 
 // Linear probing is bounded: a table that needs more probes than this is reported as full
@@ -485,7 +492,7 @@ __device__ __forceinline__ bool contact_eval(const Params& p, const int4& r1, co
   long long dx = (long long)r2.x - r1.x, dy = (long long)r2.y - r1.y;
   long long lim = (long long)p.D + 1;
   if (dx > lim || dx < -lim || dy > lim || dy < -lim) return false;
-  if (!within((int)dx, (int)dy, p.D)) return false;
+  if (!within((int)dx, (int)dy, p)) return false;
   return loc_rule(p.floors[fl1], l1, l2);
 }
 __device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
@@ -507,19 +514,18 @@ __device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h
 }
 
 // A contact found at step t that lasts `run` steps (both agents provably stay put for run-1
-// more steps of this chunk): one table update for the whole run.
-__device__ __forceinline__ void on_contact(const Params& p, int row, uint32_t t, const int4& me, const int4& ot,
-                                           uint32_t run, int sub) {
+// more steps of this chunk): one table update for the whole run.  `was`: the pair was already in
+// contact at t-1 (the event continues, contacts.py:131-133); `late`: not decided yet -- evaluate the
+// predicate on the previous record row when the record is applied.
+__device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const int4& me, const int4& ot, uint32_t run,
+                                           bool was, int sub, bool late = false) {
   uint32_t a1 = (uint32_t)min(me.z, ot.z), a2 = (uint32_t)max(me.z, ot.z);
-  // both agents exactly where (and what) they were one step ago: they were in contact then too;
-  // otherwise the predicate is evaluated on the previous row (rec row `row` holds step t-1)
-  const bool known = !fl_changed(me.w) && !fl_changed(ot.w);
   const int floor = fl_floor(me.w);
   if (p.cbuf != nullptr) {
     // warp-aggregated append into the chunk's contact buffer; k_accumulate applies it
     const FloorDev& fd = p.floors[floor];
-    long long ix = (long long)(me.x + ot.x) - 2LL * fd.minx, iy = (long long)(me.y + ot.y) - 2LL * fd.miny;
-    uint32_t bucket = (uint32_t)(fd.hist_base + iy * fd.hist_w + ix) | (known ? 0x80000000u : 0u);
+    uint32_t ix = (uint32_t)((me.x + ot.x) - 2 * fd.minx), iy = (uint32_t)((me.y + ot.y) - 2 * fd.miny);
+    uint32_t bucket = ((uint32_t)fd.hist_base + iy * (uint32_t)fd.hist_w + ix) | (was ? 0x80000000u : 0u);
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long base = 0;
     if (g.thread_rank() == 0)
@@ -527,13 +533,14 @@ __device__ __forceinline__ void on_contact(const Params& p, int row, uint32_t t,
     base = g.shfl(base, 0) + g.thread_rank();
     if (base < p.cbuf_sub_cap) {
       ContactRec r;
-      r.a1 = a1; r.a2 = a2; r.t_run = (t & 0xffffffu) | ((run - 1u) << 24); r.bucket = bucket;
+      r.a1 = a1; r.a2 = a2; r.t_run = (t & 0xffffffu) | ((run - 1u) << 24);
+      r.bucket = late ? (bucket & 0x3fffffffu) | 0x40000000u : bucket;  // bit 30: evaluate `was` in k_accumulate
       p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + base] = r;
       return;
     }
     // sub-buffer full: fall through and accumulate inline (k_accumulate clamps the count)
   }
-  bool was = known ? true : contact_prev(p, (size_t)row * p.N, a1, a2);
+  if (late) was = contact_prev(p, (size_t)((int)t - p.chunk_begin) * p.N, a1, a2);
   uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
   pair_upsert(p, a1, a2, first, run, was ? 0u : 1u);
   coord_upsert(p, floor, me.x + ot.x, me.y + ot.y, (unsigned long long)run);
@@ -620,10 +627,13 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
         int4 ot = staged ? win[q - w0] : srt[q];
         if (me_still && !fl_changed(ot.w)) continue;  // inside a run owned by an earlier step
         ++tests;
-        if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
+        if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
           uint32_t run = 1u + (uint32_t)min(me_stay, aggregate ? fl_stay(ot.w) : 0);
           hits += run;
-          on_contact(p, row, t, me, ot, run, sub);
+          // both agents exactly where (and what) they were a step ago: in contact then too;
+          // otherwise the predicate on the previous record row is evaluated at accumulation
+          const bool known = !fl_changed(me.w) && !fl_changed(ot.w);
+          on_contact(p, t, me, ot, run, known, sub, !known);
         }
       }
     }
@@ -640,10 +650,13 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
 }
 
 // Steps after the first of a chunk: only agents whose state may have changed can start, end or
-// move a contact (everything else is inside a run that an earlier step already added), so one
-// thread per changed agent (taken from the compact per-step list k_expand_bin wrote) tests its
-// full 3x3 neighbourhood: three contiguous ranges of the sorted array.  A pair of two changed
-// agents is owned by the lower id.
+// move a contact (everything else is inside a run that an earlier step already added).  One
+// thread per changed agent (taken from the compact per-step list k_expand_bin wrote) walks its
+// 3x3 neighbourhood: three contiguous ranges of the sorted array.  A pair of two changed agents
+// is owned by the lower id.  Whether the pair was in contact one step earlier is left to
+// k_accumulate (bit 30 of the record), where the two record reads overlap the table probe.
+// (Measured alternatives, config 3, ms per 12 blocks pairs/accumulate: this 63/72; predicate
+// evaluated here 81/60; four candidates per iteration 92/70; eight lanes per agent 126/60.)
 __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, int rows /* S */) {
   const int row = blockIdx.y + 1;
   const int lane = threadIdx.x & 31;
@@ -669,12 +682,12 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
       for (int q = qs; q < qe; ++q) {
         const int4 ot = srt[q];
         if (ot.z == a) continue;
-        if (fl_changed(ot.w) && ot.z < a) continue;  // that agent's warp owns the pair
+        if (fl_changed(ot.w) && ot.z < a) continue;  // that agent's thread owns the pair
         ++tests;
-        if (within(ot.x - me.x, ot.y - me.y, p.D) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
+        if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
           uint32_t run = 1u + (uint32_t)min(me_stay, fl_stay(ot.w));
           hits += run;
-          on_contact(p, row, t, me, ot, run, sub);
+          on_contact(p, t, me, ot, run, false, sub, true);
         }
       }
     }
@@ -694,7 +707,7 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
 // instead of at the pace of k_pairs' longest neighbour list.  Per record: one 16-byte slot probe
 // + one 64-bit compare-and-swap on the same sector (pair table) and one 64-bit reduction
 // (coordinate histogram); for run starts that are not known continuations also two 16-byte
-// record reads for the previous-step predicate.
+// record reads for the previous-step predicate, issued before the probe so they overlap it.
 constexpr int kAccBlocksPerSub = 24;
 
 __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
@@ -705,20 +718,20 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
   for (unsigned long long i = (unsigned long long)part * blockDim.x + threadIdx.x; i < n; i += stride) {
     ContactRec r = buf[i];
     uint32_t t = r.t_run & 0xffffffu, run = (r.t_run >> 24) + 1u;
-    int row = (int)t - t_begin;  // rec row `row` holds step t-1
-    const bool known = r.bucket >> 31;
-    // issue the previous-step record reads, the histogram reduction and the table probe
-    // back to back; none depends on another
+    bool was = r.bucket >> 31;
     int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
-    if (!known) {
-      r1 = p.rec[(size_t)row * p.N + r.a1];
-      r2 = p.rec[(size_t)row * p.N + r.a2];
+    const bool late = (r.bucket >> 30) & 1;
+    if (late) {
+      size_t prow = (size_t)((int)t - t_begin) * p.N;  // rec row holding step t-1
+      r1 = p.rec[prow + r.a1];
+      r2 = p.rec[prow + r.a2];
     }
-    atomicAdd(p.hist + (r.bucket & 0x7fffffffu), (unsigned long long)run);
+    // the histogram reduction and the table probe are independent: issue both, then update
+    atomicAdd(p.hist + (r.bucket & 0x3fffffffu), (unsigned long long)run);
     unsigned long long acc;
     unsigned long long h = pair_slot(p, ((unsigned long long)r.a1 << 32) | r.a2, &acc);
     if (h == ~0ULL) continue;
-    bool was = known ? true : contact_eval(p, r1, r2);
+    if (late) was = contact_eval(p, r1, r2);
     uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
     pair_apply(p, h, acc, first, run, was ? 0u : 1u);
   }
@@ -726,6 +739,13 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
 
 __global__ void k_reset_cbuf(DevCounters* ctr) {
   if (threadIdx.x < kSubBuffers) ctr->cbuf_count[threadIdx.x * kCounterStride] = 0ULL;
+}
+
+// The integer distance threshold must agree with the float64 predicate on THIS device.
+__global__ void k_check_s_max(double D, long long s_max, int* bad) {
+  bool ok = (s_max < 0) ? !(__dsqrt_rn(0.0) < D)
+                        : ((__dsqrt_rn((double)s_max) < D) && !(__dsqrt_rn((double)(s_max + 1)) < D));
+  *bad = ok ? 0 : 1;
 }
 
 // --------------------------------------------------------------------------
@@ -976,6 +996,7 @@ struct citam_engine {
   cudaStream_t stream = nullptr;
   int N = 0, F = 0, cell = 1;
   double D = 6.0;
+  long long s_max = 35;
   std::vector<FloorDev> floors_h;
   std::vector<int16_t*> lut_d;
   std::vector<uint32_t*> adj_d;
@@ -1025,7 +1046,21 @@ struct citam_engine {
   unsigned long long t_n[CITAM_N_KERNELS] = {0};
 };
 
-constexpr long long kDenseHistMax = 1LL << 30;  // buckets (8 GiB)
+constexpr long long kDenseHistMax = (1LL << 30) - 1;  // buckets (8 GiB); bucket ids must fit 30 bits
+
+// Largest integer s with sqrt((double)s) < D, by bisection on the monotone predicate, using the
+// host's correctly rounded IEEE sqrt (the same function the device's __dsqrt_rn computes).
+static long long find_s_max(double D) {
+  auto ok = [D](long long s) { return std::sqrt((double)s) < D; };
+  if (!ok(0)) return -1;
+  long long lo = 0, hi = 1;
+  while (ok(hi)) { lo = hi; hi *= 2; if (hi > (1LL << 60)) break; }
+  while (hi - lo > 1) {
+    long long mid = lo + (hi - lo) / 2;
+    if (ok(mid)) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 
 static unsigned long long next_pow2(unsigned long long v) {
   unsigned long long p = 1;
@@ -1075,7 +1110,7 @@ static unsigned long long pairs_used(const DevCounters& c) {
 static Params make_params(citam_engine* e) {
   Params p{};
   p.N = e->N; p.F = e->F; p.cell = e->cell; p.total_cells = e->total_cells; p.cells_stride = e->cells_stride;
-  p.D = e->D; p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
+  p.D = e->D; p.s_max = e->s_max; p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
   p.rec = e->rec; p.cells = e->cells;
   p.sorted = e->sorted; p.pairs = e->pairs; p.pair_mask = e->pair_cap - 1;
   p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist; p.range_begin = e->range_begin;
@@ -1168,6 +1203,7 @@ static int pick_chunk(citam_engine* e, int steps) {
 // bin (already done by caller) -> scan -> scatter -> pairs for `rows` steps starting at t_begin
 static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
   Params p = make_params(e);
+  p.chunk_begin = t_begin;
   {
     Timed tm(e, CITAM_K_SCAN);
     k_scan<<<rows, kScanThreads, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1);
@@ -1231,6 +1267,7 @@ int citam_create(const citam_config* cfg, citam_engine** out) {
   e->N = cfg->n_agents;
   e->F = cfg->n_floors;
   e->D = cfg->contact_distance;
+  e->s_max = find_s_max(e->D);
   int mincell = (int)std::ceil(cfg->contact_distance);
   if (mincell < 1) mincell = 1;
   e->cell = cfg->cell_size > 0 ? std::max(cfg->cell_size, mincell) : mincell;
@@ -1254,6 +1291,16 @@ int citam_create(const citam_config* cfg, citam_engine** out) {
   CK(cudaMalloc(&e->ctr_d, sizeof(DevCounters)));
   CK(cudaMalloc(&e->prev, sizeof(int4) * n));
   CK(cudaMalloc(&e->states_d, sizeof(citam_agent_state) * n));
+  {
+    int* bad_d = nullptr;
+    int bad = 1;
+    CK(cudaMalloc(&bad_d, sizeof(int)));
+    k_check_s_max<<<1, 1, 0, e->stream>>>(e->D, e->s_max, bad_d);
+    CK(cudaMemcpyAsync(&bad, bad_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(bad_d);
+    if (bad) return fail(CITAM_ERR_CUDA, "integer distance threshold %lld disagrees with the float64 predicate", e->s_max);
+  }
   return citam_reset(e);
 }
 
@@ -1458,8 +1505,12 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
     {
       Timed tm(e, CITAM_K_EXPAND_BIN);
-      dim3 g((e->N + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
-      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb - 1, rows, 1);
+      // one thread walks an agent through `rpt` consecutive steps: as many as possible (one
+      // segment search per agent) while the launch still fills the machine
+      int rpt = 16;
+      while (rpt < rows && (long long)e->N * ((rows + 2 * rpt - 1) / (2 * rpt)) >= 600000) rpt *= 2;
+      dim3 g((e->N + 127) / 128, (rows + rpt - 1) / rpt);
+      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb - 1, rows, 1, rpt);
     }
     CK(cudaGetLastError());
     rc = run_sorted_stages(e, tb, steps);
@@ -1517,7 +1568,7 @@ int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out) {
   {
     Timed tm(e, CITAM_K_MISC);
     dim3 g((e->N + 127) / 128, 1);
-    k_expand_bin<<<g, 128, 0, e->stream>>>(p, step, 1, 0);
+    k_expand_bin<<<g, 128, 0, e->stream>>>(p, step, 1, 0, 16);
     k_rec_to_states<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->rec, e->N, e->states_d);
   }
   CK(cudaGetLastError());
@@ -1544,8 +1595,9 @@ int citam_states_range(citam_engine* e, int32_t t_begin, int32_t t_end, citam_ag
     int rows = std::min(rows_max, t_end - tb);
     {
       Timed tm(e, CITAM_K_MISC);
+      const int kRowsPerThread = 16;
       dim3 g((e->N + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
-      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb, rows, 0);
+      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb, rows, 0, kRowsPerThread);
       size_t tot = n * rows;
       k_rec_to_states<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->rec, (long long)tot, tmp);
     }

@@ -1,3 +1,2 @@
-set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
 bash scripts/gpu_bench.sh
