@@ -199,6 +199,40 @@ def time_cpu_sample(g, threads, starts, steps_each):
     return len(starts) * steps_each * g.n_agents, dt
 
 
+def time_faithful_port(fac, seg_off, segs, p, D, n_sub=1500, steps=12):
+    """The reference's own formulation (oracle/port.py: scipy pdist over ALL active agents + the
+    Python pair loop, 1 core) on a sub-population, since its N x N matrix cannot hold the workload:
+    agent-steps/s at n_sub agents, for scale only (cost grows ~ N^2)."""
+    from citam_b200 import itinerary as itin
+    from oracle import port
+
+    n = min(n_sub, p["n_agents"])
+    T = p["total_timesteps"]
+    t0s = T // 2
+    so, sg = itin.slice_segments(seg_off[: n + 1], segs[: int(seg_off[n])], t0s - 1, t0s + steps)
+    from citam_b200 import synthetic as S
+
+    its = S.expand_to_reference_format(so, sg, t0s + steps)
+    its = [it[t0s - 1:] if len(it) > t0s - 1 else it[-1:] for it in its]  # start the window at t0s-1
+    minx, miny, lut = fac.lut_expected(0) if hasattr(fac, "lut_expected") else (0, 0, None)
+
+    def locate(f, x, y):
+        fx, fy = x - minx, y - miny
+        if lut is None or fx < 0 or fy < 0 or fy >= lut.shape[0] or fx >= lut.shape[1]:
+            return None
+        v = int(lut[fy, fx])
+        return None if v < 0 else v
+
+    sim = port.PortSimulation(its, fac.geometry, D, locate=locate)
+    sim.step()  # halo step
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port (reference formulation, pdist O(N^2))",
+            "sample": "%d agents x %d steps at mid-day (%.1f s)" % (n, steps, dt)}
+
+
 def run_reference(args):
     """`--impl reference`: rank 0 times the CPU restatement (the upstream reference is pure
     Python + scipy and cannot travel to the GPU box; oracle/grid_oracle.c restates its path and
@@ -320,6 +354,7 @@ def run_b200(args):
     contacts = c1["contact_steps"] - c0["contact_steps"]
     pair_tests = c1["pair_tests"] - c0["pair_tests"]
     launches = c1["kernel_launches"] - c0["kernel_launches"]
+    runs = c1["contact_runs"] - c0["contact_runs"]
 
     log("timed region done: %.1f ms, contacts %d, counters %s" % (ms, contacts, c1))
     if c1["overflow"]:
@@ -419,6 +454,7 @@ def run_b200(args):
                "sample": "oracle/grid_oracle.c, %d blocks x %d simulation steps x %d agents spread over the day (%.1f s)"
                % (len(cs), steps_each, N, dt)}
         g.close()
+        cpu["faithful_port"] = time_faithful_port(fac, seg_off, segs, p, D)
 
     if rank == 0:
         line = {
@@ -428,7 +464,8 @@ def run_b200(args):
             "config": workload_config(args, p, block),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
             "contact_steps_per_step": contacts / K, "contacts_per_agent_step": contacts / units_rank,
-            "pair_tests_per_s": pair_tests / (ms * 1e-3), "final_reduce_ms": final_reduce_ms,
+            "pair_tests_per_s": pair_tests / (ms * 1e-3), "table_updates_per_contact_step": runs / max(1, contacts),
+            "final_reduce_ms": final_reduce_ms,
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -114,7 +114,8 @@ struct DevCounters {
   unsigned long long overflow;
   unsigned long long export_cursor;
   unsigned long long stats[6];
-  unsigned long long pad[3];
+  unsigned long long contact_runs;
+  unsigned long long pad[2];
   unsigned long long cbuf_count[kSubBuffers * kCounterStride];
   unsigned long long pair_used_sub[kSubBuffers * kCounterStride];  // spread: inserts are frequent
 };
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
     for (int i = threadIdx.x; i < wlen; i += kPairThreads) win[i] = srt[w0 + i];
     __syncthreads();
   }
-  unsigned long long tests = 0, hits = 0;
+  unsigned long long tests = 0, hits = 0, runs = 0;
   if (q0 < total) {
     const FloorDev& fd = p.floors[f];
     const uint32_t t = (uint32_t)(t_begin + row);
@@ -630,6 +631,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
         if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
           uint32_t run = 1u + (uint32_t)min(me_stay, aggregate ? fl_stay(ot.w) : 0);
           hits += run;
+          ++runs;
           // both agents exactly where (and what) they were a step ago: in contact then too;
           // otherwise the predicate on the previous record row is evaluated at accumulation
           const bool known = !fl_changed(me.w) && !fl_changed(ot.w);
@@ -642,10 +644,11 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
   for (int d = 16; d > 0; d >>= 1) {
     tests += __shfl_down_sync(0xffffffffu, tests, d);
     hits += __shfl_down_sync(0xffffffffu, hits, d);
+    runs += __shfl_down_sync(0xffffffffu, runs, d);
   }
   if ((threadIdx.x & 31) == 0 && (tests | hits)) {
     atomicAdd(&p.ctr->pair_tests, tests);
-    if (hits) atomicAdd(&p.ctr->contact_steps, hits);
+    if (hits) { atomicAdd(&p.ctr->contact_steps, hits); atomicAdd(&p.ctr->contact_runs, runs); }
   }
 }
 
@@ -667,7 +670,7 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
   const int4* srt = p.sorted + (size_t)row * p.N;
   const uint32_t t = (uint32_t)(t_begin + row);
   const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
-  unsigned long long tests = 0, hits = 0;
+  unsigned long long tests = 0, hits = 0, runs = 0;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const int a = (int)p.chg_list[(size_t)row * p.N + idx];
     const int4 r = p.rec[(size_t)(row + 1) * p.N + a];
@@ -687,6 +690,7 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
         if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
           uint32_t run = 1u + (uint32_t)min(me_stay, fl_stay(ot.w));
           hits += run;
+          ++runs;
           on_contact(p, t, me, ot, run, false, sub, true);
         }
       }
@@ -695,10 +699,11 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
   for (int d = 16; d > 0; d >>= 1) {
     tests += __shfl_down_sync(0xffffffffu, tests, d);
     hits += __shfl_down_sync(0xffffffffu, hits, d);
+    runs += __shfl_down_sync(0xffffffffu, runs, d);
   }
   if (lane == 0 && (tests | hits)) {
     atomicAdd(&p.ctr->pair_tests, tests);
-    if (hits) atomicAdd(&p.ctr->contact_steps, hits);
+    if (hits) { atomicAdd(&p.ctr->contact_steps, hits); atomicAdd(&p.ctr->contact_runs, runs); }
   }
 }
 
@@ -1624,6 +1629,7 @@ int citam_get_counters(citam_engine* e, citam_counters* out) {
   out->coord_slots_used = c.coord_used;
   out->log_records = std::min<unsigned long long>(c.log_count, e->log_cap);
   out->overflow = c.overflow;
+  out->contact_runs = c.contact_runs;
   return CITAM_OK;
 }
 

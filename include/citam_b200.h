@@ -136,11 +136,12 @@ typedef struct {
 
 typedef struct {
   uint64_t agent_steps;   /* agent-steps advanced (N * steps)                     */
-  uint64_t pair_tests;    /* distance evaluations                                 */
+  uint64_t pair_tests;    /* distance evaluations actually executed               */
   uint64_t contact_steps; /* contacts found                                       */
   uint64_t kernel_launches;
   uint64_t pair_slots_used, coord_slots_used, log_records;
   uint64_t overflow;      /* bit0 pair table, bit1 coord table, bit2 log          */
+  uint64_t contact_runs;  /* table updates: a run of contact-steps of a stationary pair is one */
 } citam_counters;
 
 #define CITAM_N_KERNELS 8

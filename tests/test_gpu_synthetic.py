@@ -88,3 +88,31 @@ def test_auto_capacity_grows(synth):
     eng.run(0, T)
     assert tables_of(eng)[0] == want[0]
     eng.close()
+
+
+def test_simulation_surface_with_device_resident_itineraries(synth, tmp_path):
+    """Simulation + SegmentScheduler (no per-step Python lists), summary mode: the end-of-run files
+    hold exactly the oracle's tables."""
+    import json
+
+    from citam_b200.calculator import CloseContactsCalculator
+    from citam_b200.facility import GeometryFacility
+    from citam_b200.scheduler import SegmentScheduler
+    from citam_b200.simulation import Simulation
+    from expected_util import parse_agent_csv, parse_coord_csv, parse_pair_csv
+
+    fac, seg_off, segs, p, T, want, _ = synth
+    f = GeometryFacility(fac.geometry, "synthetic")
+    sim = Simulation(f, T, p["n_agents"], calculators=[CloseContactsCalculator(f, 6.0, full_fidelity=False)],
+                     scheduler=SegmentScheduler(f, T, seg_off, segs))
+    sim.block_steps = 1000
+    sim.run_serial(str(tmp_path), "s", "r")
+    pairs = parse_pair_csv(open(tmp_path / "pair_contact.csv", "rb").read())
+    assert pairs == [(a, b, n, d) for a, b, _, n, d in want[0]]
+    assert parse_agent_csv(open(tmp_path / "contact_dist_per_agent.csv", "rb").read()) == want[2]
+    for fl in range(p["n_floors"]):
+        got = parse_coord_csv(open(tmp_path / ("floor_%d" % fl) / "contact_dist_per_coord.csv", "rb").read())
+        assert got == {(sx / 2.0, sy / 2.0): c for (f2, sx, sy), c in want[1].items() if f2 == fl}
+    st = json.load(open(tmp_path / "statistics.json"))["data"]
+    assert st[3]["value"] == len({a for r in want[0] for a in r[:2]})
+    assert sim.current_step == T
