@@ -156,21 +156,26 @@ struct Params {
 #define OVF_FIELD 16ULL
 
 // state word: bits 0-14 space index (0x7fff = none); bit 15 "changed": the agent is NOT known to
-// be exactly where it was one step earlier (it moves, or this is the first step of its
-// segment); bits 16-23 "stay": for how many following steps of this chunk the state is
-// guaranteed identical (same zero-velocity segment); bits 24-30 floor; bit 31 = not in the
-// facility.  changed/stay come from the segment store alone, so they agree with each other:
-// changed(t+k) == 0 for k = 1..stay(t) and changed(t+stay+1) == 1 (or the chunk ends).
+// be exactly where it was one step earlier (it moves, or this is the first step of its segment);
+// bits 16-23: for a still agent "stay" = for how many following steps of this chunk the state is
+// guaranteed identical (same zero-velocity segment); for a moving agent (bit 30) the step it
+// just made, (dx+8) | (dy+8) << 4, or 0 when that is not known here (first step of a segment, a
+// stride beyond +-7); bits 24-29 floor; bit 31 = not in the facility.  changed/stay come from the
+// segment store alone, so they agree with each other: changed(t+k) == 0 for k = 1..stay(t) and
+// changed(t+stay+1) == 1 (or the chunk ends).
 constexpr int kMaxChunk = 256;  // stay must fit 8 bits
-__device__ __forceinline__ int32_t pack_fl(int floor, int loc, int changed = 1, int stay = 0) {
+constexpr int kMaxFloors = 63;
+__device__ __forceinline__ int32_t pack_fl(int floor, int loc, int changed = 1, int stay = 0, int moving = 0) {
   if (floor < 0) return (int32_t)0x8000ffffu;
-  return (int32_t)(((uint32_t)(floor & 0x7f) << 24) | ((uint32_t)(stay & 0xff) << 16) | ((uint32_t)(changed & 1) << 15) |
-                   ((uint32_t)loc & 0x7fffu));
+  return (int32_t)(((uint32_t)(moving & 1) << 30) | ((uint32_t)(floor & 0x3f) << 24) | ((uint32_t)(stay & 0xff) << 16) |
+                   ((uint32_t)(changed & 1) << 15) | ((uint32_t)loc & 0x7fffu));
 }
-__device__ __forceinline__ int fl_floor(int32_t fl) { return fl < 0 ? -1 : (fl >> 24) & 0x7f; }
+__device__ __forceinline__ int fl_floor(int32_t fl) { return fl < 0 ? -1 : (fl >> 24) & 0x3f; }
 __device__ __forceinline__ int fl_loc(int32_t fl) { int v = fl & 0x7fff; return v == 0x7fff ? -1 : v; }
 __device__ __forceinline__ bool fl_changed(int32_t fl) { return (fl >> 15) & 1; }
-__device__ __forceinline__ int fl_stay(int32_t fl) { return (fl >> 16) & 0xff; }
+__device__ __forceinline__ bool fl_moving(int32_t fl) { return (fl >> 30) & 1; }
+__device__ __forceinline__ int fl_stay(int32_t fl) { return fl_moving(fl) ? 0 : (fl >> 16) & 0xff; }
+__device__ __forceinline__ int fl_step_code(int32_t fl) { return fl_moving(fl) ? (fl >> 16) & 0xff : 0; }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33;
@@ -245,16 +250,16 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
     const bool still = s.w == 0;
     int changed = !(still && dt >= 1);
     int stay = still ? min(min(next_t0 - 1 - t, rows - 1 - row), kMaxChunk - 1) : 0;
+    if (!still) {  // the step just made, when it is this segment's stride
+      int vx = (int)(int16_t)(s.w & 0xffff), vy = (int)(int16_t)((uint32_t)s.w >> 16);
+      stay = (dt >= 1 && vx >= -7 && vx <= 7 && vy >= -7 && vy <= 7) ? ((vx + 8) | ((vy + 8) << 4)) : 0;
+    }
     uint32_t rk = 0;
     if (do_bin && row >= 1 && loc >= 0) {
       int key = cell_of(p.floors[f], p.cell, x, y);
       rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
-      if (changed && p.chg_count != nullptr) {
-        uint32_t ix = atomicAdd(&p.chg_count[(row - 1) * 32], 1u);
-        p.chg_list[(size_t)(row - 1) * p.N + ix] = (uint32_t)a;
-      }
     }
-    p.rec[o] = make_int4(x, y, pack_fl(f, loc, changed, stay), (int)rk);
+    p.rec[o] = make_int4(x, y, pack_fl(f, loc, changed, stay, still ? 0 : 1), (int)rk);
   }
 }
 
@@ -372,6 +377,28 @@ __global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */) {
   int key = cell_of(p.floors[f], p.cell, r.x, r.y);
   uint32_t dest = p.cells[(size_t)row * p.cells_stride + key] + (uint32_t)r.w;
   p.sorted[(size_t)row * p.N + dest] = make_int4(r.x, r.y, a, r.z);
+}
+
+// K3b: per step, the sorted positions of the agents whose state may have changed, compacted in
+// CELL ORDER (each warp appends its 32 consecutive sorted positions' hits in one piece), so that
+// neighbouring threads of k_pairs_changed work on neighbouring agents: their candidate ranges
+// overlap (L1 hits) and their histogram buckets share sectors.
+__global__ void __launch_bounds__(256) k_select_changed(Params p, int rows /* S */) {
+  const int row = blockIdx.y + 1;  // the first step of a chunk is handled by k_pairs in full
+  if (row >= rows) return;
+  const int total = (int)p.cells[(size_t)row * p.cells_stride + p.total_cells];
+  const int lane = threadIdx.x & 31;
+  for (int q0 = blockIdx.x * blockDim.x; q0 < total; q0 += gridDim.x * blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    bool sel = false;
+    if (q < total) sel = fl_changed(p.sorted[(size_t)row * p.N + q].w);
+    unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (m == 0) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&p.chg_count[row * 32], (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (sel) p.chg_list[(size_t)row * p.N + base + __popc(m & ((1u << lane) - 1))] = (uint32_t)q;
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -654,13 +681,19 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
 
 // Steps after the first of a chunk: only agents whose state may have changed can start, end or
 // move a contact (everything else is inside a run that an earlier step already added).  One
-// thread per changed agent (taken from the compact per-step list k_expand_bin wrote) walks its
-// 3x3 neighbourhood: three contiguous ranges of the sorted array.  A pair of two changed agents
-// is owned by the lower id.  Whether the pair was in contact one step earlier is left to
-// k_accumulate (bit 30 of the record), where the two record reads overlap the table probe.
-// (Measured alternatives, config 3, ms per 12 blocks pairs/accumulate: this 63/72; predicate
-// evaluated here 81/60; four candidates per iteration 92/70; eight lanes per agent 126/60.)
+// thread per changed agent (taken, in cell order, from the per-step list of k_select_changed) walks
+// its 3x3 neighbourhood: three contiguous ranges of the sorted array.  A pair of two changed agents
+// is owned by the lower id.  Hits are parked in shared memory and appended to the contact buffer
+// once per warp and agent batch (one atomic for the warp, contiguous 16-byte stores) instead of
+// one atomic round trip per hit inside the divergent loop.  Whether the pair was in contact one
+// step earlier is left to k_accumulate (bit 30 of the record), where the two record reads overlap
+// the table probe.  (Measured alternatives, config 3, ms per 12 blocks pairs/accumulate: deciding
+// it here from the packed stride 68/59 vs 55/69; four candidates per iteration 92/70; eight lanes
+// per agent 126/60.)
+constexpr int kHitSlots = 6;
+
 __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, int rows /* S */) {
+  __shared__ ContactRec hitbuf[256 * kHitSlots];
   const int row = blockIdx.y + 1;
   const int lane = threadIdx.x & 31;
   const uint32_t n = p.chg_count[row * 32];
@@ -670,28 +703,68 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
   const int4* srt = p.sorted + (size_t)row * p.N;
   const uint32_t t = (uint32_t)(t_begin + row);
   const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
+  const bool buffered = p.cbuf != nullptr;
+  ContactRec* mine = hitbuf + threadIdx.x * kHitSlots;
   unsigned long long tests = 0, hits = 0, runs = 0;
-  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const int a = (int)p.chg_list[(size_t)row * p.N + idx];
-    const int4 r = p.rec[(size_t)(row + 1) * p.N + a];
-    const int4 me = make_int4(r.x, r.y, a, r.z);
-    const int f = fl_floor(r.z), loc = fl_loc(r.z), me_stay = fl_stay(r.z);
-    const FloorDev& fd = p.floors[f];
-    const int cx = (r.x - fd.minx) / p.cell, cy = (r.y - fd.miny) / p.cell;
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
-    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, fd.ncy - 1); ++yy) {
-      const int rb = fd.cell_base + yy * fd.ncx;
-      const int qs = (int)cs[rb + x0], qe = (int)cs[rb + x1 + 1];
-      for (int q = qs; q < qe; ++q) {
-        const int4 ot = srt[q];
-        if (ot.z == a) continue;
-        if (fl_changed(ot.w) && ot.z < a) continue;  // that agent's thread owns the pair
-        ++tests;
-        if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
-          uint32_t run = 1u + (uint32_t)min(me_stay, fl_stay(ot.w));
-          hits += run;
-          ++runs;
-          on_contact(p, t, me, ot, run, false, sub, true);
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t idx = base + threadIdx.x;
+    int nh = 0;
+    if (idx < n) {
+      const int4 me = srt[p.chg_list[(size_t)row * p.N + idx]];
+      const int a = me.z;
+      const int f = fl_floor(me.w), loc = fl_loc(me.w), me_stay = fl_stay(me.w);
+      const FloorDev& fd = p.floors[f];
+      const int cx = (me.x - fd.minx) / p.cell, cy = (me.y - fd.miny) / p.cell;
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
+      const uint32_t hbase = (uint32_t)fd.hist_base - (uint32_t)(2 * fd.miny) * (uint32_t)fd.hist_w - (uint32_t)(2 * fd.minx);
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, fd.ncy - 1); ++yy) {
+        const int rb = fd.cell_base + yy * fd.ncx;
+        const int qs = (int)cs[rb + x0], qe = (int)cs[rb + x1 + 1];
+        for (int q = qs; q < qe; ++q) {
+          const int4 ot = srt[q];
+          if (ot.z == a) continue;
+          if (fl_changed(ot.w) && ot.z < a) continue;  // that agent's thread owns the pair
+          ++tests;
+          if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
+            uint32_t run = 1u + (uint32_t)min(me_stay, fl_stay(ot.w));
+            hits += run;
+            ++runs;
+            if (buffered && nh < kHitSlots) {
+              ContactRec r;
+              r.a1 = (uint32_t)min(a, ot.z); r.a2 = (uint32_t)max(a, ot.z);
+              r.t_run = (t & 0xffffffu) | ((run - 1u) << 24);
+              r.bucket = ((hbase + (uint32_t)(me.y + ot.y) * (uint32_t)fd.hist_w + (uint32_t)(me.x + ot.x)) & 0x3fffffffu) | 0x40000000u;
+              mine[nh++] = r;
+            } else {
+              on_contact(p, t, me, ot, run, false, sub, true);
+            }
+          }
+        }
+      }
+    }
+    if (buffered) {
+      // one reservation for the whole warp
+      int off = nh;
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, off, d);
+        if (lane >= d) off += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, off, 31);
+      if (total > 0) {
+        unsigned long long wbase = 0;
+        if (lane == 31) wbase = atomicAdd(&p.ctr->cbuf_count[sub * kCounterStride], (unsigned long long)total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31) + (unsigned long long)(off - nh);
+        for (int j = 0; j < nh; ++j) {
+          if (wbase + j < p.cbuf_sub_cap) {
+            p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + wbase + j] = mine[j];
+          } else {  // sub-buffer full: apply inline (k_accumulate clamps the count)
+            const ContactRec r = mine[j];
+            const uint32_t rt = r.t_run & 0xffffffu, rrun = (r.t_run >> 24) + 1u;
+            bool was = contact_prev(p, (size_t)((int)rt - p.chunk_begin) * p.N, r.a1, r.a2);
+            uint32_t first = (!was || (int32_t)rt == p.range_begin) ? rt : NO_STEP;
+            pair_upsert(p, r.a1, r.a2, first, rrun, was ? 0u : 1u);
+            atomicAdd(p.hist + (r.bucket & 0x3fffffffu), (unsigned long long)rrun);
+          }
         }
       }
     }
@@ -1217,6 +1290,10 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     Timed tm(e, CITAM_K_SCATTER);
     dim3 g((e->N + 255) / 256, rows);
     k_scatter<<<g, 256, 0, e->stream>>>(p, rows);
+    if (p.chg_count != nullptr && rows > 1) {
+      dim3 g3((unsigned)std::min(296, std::max(1, (e->N + 255) / 256)), rows - 1);
+      k_select_changed<<<g3, 256, 0, e->stream>>>(p, rows);
+    }
   }
   {
     Timed tm(e, CITAM_K_PAIRS);
@@ -1225,7 +1302,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     dim3 g((e->N + 255) / 256, agg ? 1 : rows);
     k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0);
     if (agg && rows > 1) {
-      dim3 g2((unsigned)std::min(2048, std::max(1, (e->N + 255) / 256)), rows - 1);
+      dim3 g2((unsigned)std::min(592, std::max(1, (e->N + 255) / 256)), rows - 1);
       k_pairs_changed<<<g2, 256, 0, e->stream>>>(p, t_begin, rows);
     }
   }
@@ -1257,8 +1334,8 @@ const char* citam_last_error(void) { return g_err.c_str(); }
 
 int citam_create(const citam_config* cfg, citam_engine** out) {
   if (!cfg || !out) return fail(CITAM_ERR_INVALID, "null argument");
-  if (cfg->n_agents <= 0 || cfg->n_floors <= 0 || cfg->n_floors > 127)
-    return fail(CITAM_ERR_INVALID, "n_agents must be > 0 and n_floors in 1..127");
+  if (cfg->n_agents <= 0 || cfg->n_floors <= 0 || cfg->n_floors > kMaxFloors)
+    return fail(CITAM_ERR_INVALID, "n_agents must be > 0 and n_floors in 1..63");
   if (!(cfg->contact_distance >= 0.0) || cfg->contact_distance > 1e6)
     return fail(CITAM_ERR_INVALID, "contact_distance out of range");
   int ndev = 0;

@@ -18,7 +18,7 @@ import numpy as np
 from ._lib import SEGMENT
 
 MAX_STEP = (1 << 24) - 1
-MAX_FLOOR = 126
+MAX_FLOOR = 62
 
 
 def pack(itineraries: Sequence[Sequence]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:

@@ -44,7 +44,7 @@ typedef struct citam_engine citam_engine;
 /* ---- configuration ---------------------------------------------------- */
 typedef struct {
   int32_t n_agents;         /* agents 0..n-1 in schedule order (simulation.py:277-289) */
-  int32_t n_floors;
+  int32_t n_floors;         /* 1..63 */
   double contact_distance;  /* CloseContactsCalculator.contact_distance, strict `<`
                                (close_contacts_calculator.py:21-28,171)                */
   int32_t cell_size;        /* uniform-grid cell edge in drawing units; 0 = ceil(D)    */
