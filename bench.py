@@ -208,7 +208,7 @@ def time_faithful_port(fac, seg_off, segs, p, D, n_sub=1500, steps=12):
 
     n = min(n_sub, p["n_agents"])
     T = p["total_timesteps"]
-    t0s = T // 2
+    t0s = (T // max(1, p["n_shifts"])) // 2  # the middle of the first shift
     so, sg = itin.slice_segments(seg_off[: n + 1], segs[: int(seg_off[n])], t0s - 1, t0s + steps)
     from citam_b200 import synthetic as S
 

@@ -312,23 +312,27 @@ __global__ void k_fill_inactive(int4* rec, int N) {
 }
 
 // --------------------------------------------------------------------------
-// K2: per-step exclusive scan of the cell histogram (one CTA per step, in place).
+// K2: per-step exclusive scan of the cell histogram, in place.
 // cells[row][0..total_cells) counts -> starts; cells[row][total_cells] = located agents.
-// Warp shuffles scan 4 cells per thread; warp totals are combined through shared memory.
+// A row is cut into `parts` pieces so that rows x parts CTAs fill the machine: k_scan scans its
+// piece (warp shuffles over 4 cells per thread, warp totals through shared memory) and leaves
+// the piece total in part_sums; k_scan_add adds the totals of the pieces before it.
 // --------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;
 
-__global__ void __launch_bounds__(kScanThreads) k_scan(uint32_t* cells, int stride, int n /* total_cells+1 */) {
+__global__ void __launch_bounds__(kScanThreads) k_scan(uint32_t* cells, int stride, int n /* total_cells+1 */,
+                                                       int part_len4, uint32_t* part_sums) {
   __shared__ uint32_t warp_off[32];
   __shared__ uint32_t s_tot;
-  uint4* c4 = reinterpret_cast<uint4*>(cells + (size_t)blockIdx.x * stride);
+  uint4* c4 = reinterpret_cast<uint4*>(cells + (size_t)blockIdx.y * stride);
   const int n4 = (n + 3) >> 2;  // stride is a multiple of 4 and the padding is zero
+  const int begin = blockIdx.x * part_len4, end = min(n4, begin + part_len4);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t carry = 0;
-  for (int base = 0; base < n4; base += kScanThreads) {
+  for (int base = begin; base < end; base += kScanThreads) {
     int i = base + threadIdx.x;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (i < n4) v = c4[i];
+    if (i < end) v = c4[i];
     uint32_t sum = v.x + v.y + v.z + v.w;
     uint32_t inc = sum;
 #pragma unroll
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(uint32_t* cells, int stri
     }
     __syncthreads();
     uint32_t ex = carry + warp_off[w] + (inc - sum);
-    if (i < n4) {
+    if (i < end) {
       uint4 o;
       o.x = ex;
       o.y = ex + v.x;
@@ -361,6 +365,23 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(uint32_t* cells, int stri
     }
     carry += s_tot;
     __syncthreads();
+  }
+  if (threadIdx.x == 0) part_sums[blockIdx.y * gridDim.x + blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_scan_add(uint32_t* cells, int stride, int n, int part_len4,
+                                                  const uint32_t* part_sums) {
+  const int part = blockIdx.x + 1;  // piece 0 needs no offset
+  uint32_t off = 0;
+  for (int q = 0; q < part; ++q) off += part_sums[blockIdx.y * (gridDim.x + 1) + q];
+  if (off == 0) return;
+  uint4* c4 = reinterpret_cast<uint4*>(cells + (size_t)blockIdx.y * stride);
+  const int n4 = (n + 3) >> 2;
+  const int begin = part * part_len4, end = min(n4, begin + part_len4);
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    uint4 v = c4[i];
+    v.x += off; v.y += off; v.z += off; v.w += off;
+    c4[i] = v;
   }
 }
 
@@ -1106,7 +1127,7 @@ struct citam_engine {
   unsigned long long log_cap = 0;
   ContactRec* cbuf = nullptr;
   unsigned long long cbuf_cap = 0;
-  uint32_t *chg_list = nullptr, *chg_count = nullptr;
+  uint32_t *chg_list = nullptr, *chg_count = nullptr, *part_sums = nullptr;
   unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
   DevCounters* ctr_d = nullptr;
@@ -1124,6 +1145,7 @@ struct citam_engine {
   unsigned long long t_n[CITAM_N_KERNELS] = {0};
 };
 
+constexpr int kMaxScanParts = 32;
 constexpr long long kDenseHistMax = (1LL << 30) - 1;  // buckets (8 GiB); bucket ids must fit 30 bits
 
 // Largest integer s with sqrt((double)s) < D, by bisection on the monotone predicate, using the
@@ -1202,8 +1224,8 @@ static Params make_params(citam_engine* e) {
 
 static void free_chunk(citam_engine* e) {
   cudaFree(e->rec); cudaFree(e->cells);
-  cudaFree(e->sorted); cudaFree(e->cbuf); cudaFree(e->chg_list); cudaFree(e->chg_count);
-  e->chg_list = e->chg_count = nullptr;
+  cudaFree(e->sorted); cudaFree(e->cbuf); cudaFree(e->chg_list); cudaFree(e->chg_count); cudaFree(e->part_sums);
+  e->chg_list = e->chg_count = e->part_sums = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -1262,6 +1284,7 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->cbuf, sizeof(ContactRec) * e->cbuf_cap));
   CK(cudaMalloc(&e->chg_list, sizeof(uint32_t) * n * S));
   CK(cudaMalloc(&e->chg_count, sizeof(uint32_t) * 32 * S));
+  CK(cudaMalloc(&e->part_sums, sizeof(uint32_t) * kMaxScanParts * S));
   e->S = S;
   return CITAM_OK;
 }
@@ -1284,7 +1307,15 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
   p.chunk_begin = t_begin;
   {
     Timed tm(e, CITAM_K_SCAN);
-    k_scan<<<rows, kScanThreads, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1);
+    const int n4 = (e->total_cells + 1 + 3) >> 2;
+    int parts = std::max(1, std::min(kMaxScanParts, std::min((296 + rows - 1) / rows, (n4 + 4095) / 4096)));
+    int part_len4 = (n4 + parts - 1) / parts;
+    parts = (n4 + part_len4 - 1) / part_len4;
+    k_scan<<<dim3(parts, rows), kScanThreads, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
+                                                              e->part_sums);
+    if (parts > 1)
+      k_scan_add<<<dim3(parts - 1, rows), 256, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
+                                                               e->part_sums);
   }
   {
     Timed tm(e, CITAM_K_SCATTER);
