@@ -68,6 +68,7 @@ class CloseContactsCalculator(Calculator):
         self._agents = None
         self._files = []
         self._durations = None
+        self.heatmap_max_points = 200_000  # one svg circle per coordinate: skipped beyond this
 
     # -- protocol -----------------------------------------------------------------------------
     @property
@@ -173,8 +174,8 @@ class CloseContactsCalculator(Calculator):
         return ids, n
 
     def save_to_files(self, agents, work_directory: str) -> None:
-        """close_contacts_calculator.py:250-318 (the svg heatmap is not written: map.svg comes from
-        the floorplan exporter, which is outside this path)."""
+        """close_contacts_calculator.py:250-318, including floor_k/heatmap.svg when floor_k/map.svg
+        exists (citam_b200/svg.py)."""
         ids, n = self.extract_contact_distribution_per_agent(agents)
         with open(os.path.join(work_directory, "contact_dist_per_agent.csv"), "w") as f:
             f.write("agent_ID,Number_of_Contacts\n")
@@ -193,3 +194,7 @@ class CloseContactsCalculator(Calculator):
                 f.write("x,y,n_contacts\n")
                 for (x, y), c in per_coord.items():
                     f.write(str(x) + "," + str(y) + "," + str(c) + "\n")
+            if os.path.isfile(os.path.join(d, "map.svg")) and len(per_coord) <= self.heatmap_max_points:
+                from . import svg
+
+                svg.write_heatmap_svg(per_coord, d, self.contact_distance)

@@ -84,11 +84,10 @@ class Simulation:
             self.agents[agent.unique_id] = agent
 
     def run_serial(self, workdir, sim_name: str, run_name: str) -> None:
-        """simulation.py:215-246 (map.svg export belongs to the floorplan tooling and is skipped)."""
+        """simulation.py:215-246 ."""
         self.create_sim_hash()
         self.save_manifest(workdir, sim_name, run_name)
-        for f in range(self.facility.number_of_floors):
-            os.makedirs(os.path.join(workdir, "floor_" + str(f)), exist_ok=True)
+        self.save_maps(workdir)
         self.create_agents()
         self.save_schedules(workdir)
         for calculator in self.calculators:
@@ -251,6 +250,19 @@ class Simulation:
         }
         with open(os.path.join(work_directory, "manifest.json"), "w") as f:
             json.dump(manifest, f, indent=4)
+
+    def save_maps(self, work_directory) -> None:
+        """simulation.py:422-458: floor_k/map.svg (walls, `<g id="root">`, the upstream viewBox rule)."""
+        from . import svg
+        from .facility import geometry_from_facility
+
+        geom = geometry_from_facility(self.facility)
+        for f in range(self.facility.number_of_floors):
+            d = os.path.join(work_directory, "floor_" + str(f))
+            os.makedirs(d, exist_ok=True)
+            fp = self.facility.floorplans[f]
+            svg.write_map_svg(svg.floor_walls(geom["floors"][f]), os.path.join(d, "map.svg"),
+                              [fp.minx - 50, fp.miny - 50, fp.maxx + 50, fp.maxy + 50])
 
     def save_schedules(self, work_directory) -> None:
         """simulation.py:460-486."""

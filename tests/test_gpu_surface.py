@@ -63,6 +63,15 @@ def test_run_serial_block_path_files_byte_identical(name, tmp_path):
         assert k in m
     want_dur = parse_agent_csv(expected(case, "contact_dist_per_agent.csv"))
     assert [a.cumulative_properties["contact_duration"] for a in sim.agents.values()] == want_dur
+    # dashboard svgs: one circle per contact coordinate on top of the floor map
+    import xml.etree.ElementTree as ET
+
+    for f in range(len(case["geometry"]["floors"])):
+        d = os.path.join(str(tmp_path), "floor_%d" % f)
+        assert ET.parse(os.path.join(d, "map.svg")).getroot()[0].attrib["id"] == "root"
+        g = ET.parse(os.path.join(d, "heatmap.svg")).getroot()[0]
+        n_coords = len(parse_coord_csv(expected(case, "floor_%d/contact_dist_per_coord.csv" % f)))
+        assert sum(1 for e in g if e.tag.endswith("circle")) == n_coords
 
 
 @pytest.mark.parametrize("name", ["twofloor", "crafted"])

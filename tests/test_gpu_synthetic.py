@@ -116,3 +116,26 @@ def test_simulation_surface_with_device_resident_itineraries(synth, tmp_path):
     st = json.load(open(tmp_path / "statistics.json"))["data"]
     assert st[3]["value"] == len({a for r in want[0] for a in r[:2]})
     assert sim.current_step == T
+
+
+def test_replica_sweep_matches_oracle_per_replica():
+    """BASELINE config 4 in small: independent replicas (occupancy x shifts x distance x seed) run
+    concurrently on one GPU; each replica's statistics equal the C oracle's."""
+    from citam_b200 import sweep
+    from citam_b200 import synthetic as S
+    from oracle import port
+
+    specs = [s for s in sweep.make_sweep(10, total_timesteps=900, offices=600)]
+    assert len({(s.n_agents, s.n_shifts, s.contact_distance) for s in specs}) == 10
+    res = sweep.run_sweep(specs, workers=3)
+    assert [r["replica"] for r in res] == list(range(10))
+    fac = S.SyntheticFacility(1)
+    for spec, r in zip(specs, res):
+        seg_off, segs = S.make_itineraries(fac, spec.n_agents, spec.total_timesteps, n_shifts=spec.n_shifts, seed=spec.seed)
+        g = grid_oracle_for(fac.geometry, spec.contact_distance, seg_off, segs)
+        g.run(0, spec.total_timesteps, 4)
+        pairs = g.pairs()
+        rows = [(str(a), str(b), int(n), int(d)) for a, b, n, d in zip(pairs["a1"], pairs["a2"], pairs["n_events"], pairs["duration"])]
+        want = {d["name"]: d["value"] for d in port.statistics_from_pairs(rows)}
+        assert r["statistics"] == want, spec
+        assert r["contact_steps"] == g.contact_steps

@@ -140,3 +140,25 @@ def test_statistics_from_sums_matches_python_rounding():
     assert v == [774.45, 21.8, 38.72, 20, 9.5, 25]  # SURVEY.md Appendix B.5 (reference, seed 0)
     z = dict(total_duration=0, n_pairs=0, n_agents_with_contacts=0, sum_events_per_agent=0, max_events_per_agent=0)
     assert [d["value"] for d in statistics_from_sums(z)] == [0.0, 0, 0.0, 0, 0, 0]
+
+
+def test_svg_writers(tmp_path):
+    import xml.etree.ElementTree as ET
+
+    from citam_b200 import svg
+
+    c = load_case("twofloor")
+    walls = svg.floor_walls(c["geometry"]["floors"][0])
+    assert len(walls) > 10 and len({tuple(w) for w in walls}) == len(walls)
+    d = str(tmp_path)
+    with pytest.raises(FileNotFoundError):
+        svg.write_heatmap_svg({(1.0, 2.0): 3}, d, 6.0)
+    svg.write_map_svg(walls, os.path.join(d, "map.svg"), [-50, -170, 400, 250])
+    root = ET.parse(os.path.join(d, "map.svg")).getroot()
+    assert root.attrib["viewBox"] == "-50 -170 400 250" and root[0].attrib["id"] == "root" and len(root[0]) == len(walls)
+    svg.write_heatmap_svg({(1.0, 2.0): 3, (5.5, 7.0): 1}, d, 6.0)
+    g = ET.parse(os.path.join(d, "heatmap.svg")).getroot()[0]
+    circles = [e for e in g if e.tag.endswith("circle")]
+    assert len(circles) == 2 and circles[0].attrib["r"] == "6.0" and circles[0].attrib["filter"] == "url(#blurMe)"
+    assert circles[0].attrib["fill"] == svg.rdylgn_hex(0.0) == "#a50026" and svg.rdylgn_hex(1.0) == "#006837"
+    assert any(e.tag.endswith("filter") and e.attrib["id"] == "blurMe" for e in g)
