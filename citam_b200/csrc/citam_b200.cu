@@ -701,24 +701,33 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
 }
 
 // Steps after the first of a chunk: only agents whose state may have changed can start, end or
-// move a contact (everything else is inside a run that an earlier step already added).  One
-// thread per changed agent (taken, in cell order, from the per-step list of k_select_changed) walks
-// its 3x3 neighbourhood: three contiguous ranges of the sorted array.  A pair of two changed agents
-// is owned by the lower id.  Hits are parked in shared memory and appended to the contact buffer
-// once per warp and agent batch (one atomic for the warp, contiguous 16-byte stores) instead of
-// one atomic round trip per hit inside the divergent loop.  Whether the pair was in contact one
-// step earlier is left to k_accumulate (bit 30 of the record), where the two record reads overlap
-// the table probe.  (Measured alternatives, config 3, ms per 12 blocks pairs/accumulate: deciding
-// it here from the packed stride 68/59 vs 55/69; four candidates per iteration 92/70; eight lanes
-// per agent 126/60.)
+// move a contact (everything else is inside a run that an earlier step already added).  A block
+// takes a batch of 256 changed agents (in cell order, from the per-step list of k_select_changed);
+// every agent's 3x3 neighbourhood is three contiguous ranges of the sorted array.  The tests of the
+// whole batch are flattened into one index space (block scan of the candidate counts, binary search
+// in shared memory), so all 32 lanes of a warp test a candidate each, whatever the neighbour counts
+// are, and consecutive lanes read consecutive sorted records.  A pair of two changed agents is
+// owned by the lower id.  Hits are parked in shared memory and appended to the contact buffer once
+// per warp and batch (one atomic for the warp, contiguous 16-byte stores).  Whether the pair was in
+// contact one step earlier is left to k_accumulate (bit 30 of the record), where the two record
+// reads overlap the table probe.  (Measured alternatives, config 3, ms per 12 blocks
+// pairs/accumulate: one thread per agent 47/64; deciding the previous-step predicate here from the
+// packed stride 68/59; four candidates per iteration 92/70; eight lanes per agent 126/60.)
 constexpr int kHitSlots = 6;
+constexpr int kPC = 256;
 
-__global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, int rows /* S */) {
-  __shared__ ContactRec hitbuf[256 * kHitSlots];
+__global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, int rows /* S */) {
+  __shared__ ContactRec hitbuf[kPC * kHitSlots];
+  __shared__ int4 s_me[kPC];
+  __shared__ int s_qs[3][kPC];
+  __shared__ int s_l0[kPC], s_l01[kPC];
+  __shared__ uint32_t s_hb[kPC];
+  __shared__ int s_off[kPC + 1];
+  __shared__ int s_warp[kPC / 32];
   const int row = blockIdx.y + 1;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = p.chg_count[row * 32];
-  if (blockIdx.x * blockDim.x >= n) return;
+  if (blockIdx.x * kPC >= n) return;
   if (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) return;
   const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
   const int4* srt = p.sorted + (size_t)row * p.N;
@@ -727,40 +736,73 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
   const bool buffered = p.cbuf != nullptr;
   ContactRec* mine = hitbuf + threadIdx.x * kHitSlots;
   unsigned long long tests = 0, hits = 0, runs = 0;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+  for (uint32_t base = blockIdx.x * kPC; base < n; base += gridDim.x * kPC) {
+    // ---- phase 1: one thread per agent describes its candidate ranges
     const uint32_t idx = base + threadIdx.x;
-    int nh = 0;
+    int total = 0;
     if (idx < n) {
       const int4 me = srt[p.chg_list[(size_t)row * p.N + idx]];
-      const int a = me.z;
-      const int f = fl_floor(me.w), loc = fl_loc(me.w), me_stay = fl_stay(me.w);
-      const FloorDev& fd = p.floors[f];
+      const FloorDev& fd = p.floors[fl_floor(me.w)];
       const int cx = (me.x - fd.minx) / p.cell, cy = (me.y - fd.miny) / p.cell;
       const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
-      const uint32_t hbase = (uint32_t)fd.hist_base - (uint32_t)(2 * fd.miny) * (uint32_t)fd.hist_w - (uint32_t)(2 * fd.minx);
-      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, fd.ncy - 1); ++yy) {
-        const int rb = fd.cell_base + yy * fd.ncx;
-        const int qs = (int)cs[rb + x0], qe = (int)cs[rb + x1 + 1];
-        for (int q = qs; q < qe; ++q) {
-          const int4 ot = srt[q];
-          if (ot.z == a) continue;
-          if (fl_changed(ot.w) && ot.z < a) continue;  // that agent's thread owns the pair
-          ++tests;
-          if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
-            uint32_t run = 1u + (uint32_t)min(me_stay, fl_stay(ot.w));
-            hits += run;
-            ++runs;
-            if (buffered && nh < kHitSlots) {
-              ContactRec r;
-              r.a1 = (uint32_t)min(a, ot.z); r.a2 = (uint32_t)max(a, ot.z);
-              r.t_run = (t & 0xffffffu) | ((run - 1u) << 24);
-              r.bucket = ((hbase + (uint32_t)(me.y + ot.y) * (uint32_t)fd.hist_w + (uint32_t)(me.x + ot.x)) & 0x3fffffffu) | 0x40000000u;
-              mine[nh++] = r;
-            } else {
-              on_contact(p, t, me, ot, run, false, sub, true);
-            }
-          }
-        }
+      const int rb = fd.cell_base + cy * fd.ncx;
+      const bool up = cy + 1 < fd.ncy, dn = cy > 0;
+      const int rbu = up ? rb + fd.ncx : rb, rbd = dn ? rb - fd.ncx : rb;
+      const int q0 = (int)cs[rbd + x0], l0 = dn ? (int)cs[rbd + x1 + 1] - q0 : 0;
+      const int q1 = (int)cs[rb + x0], l1 = (int)cs[rb + x1 + 1] - q1;
+      const int q2 = (int)cs[rbu + x0], l2 = up ? (int)cs[rbu + x1 + 1] - q2 : 0;
+      s_me[threadIdx.x] = me;
+      s_qs[0][threadIdx.x] = q0; s_qs[1][threadIdx.x] = q1; s_qs[2][threadIdx.x] = q2;
+      s_l0[threadIdx.x] = l0; s_l01[threadIdx.x] = l0 + l1;
+      s_hb[threadIdx.x] = (uint32_t)fd.hist_base - (uint32_t)(2 * fd.miny) * (uint32_t)fd.hist_w - (uint32_t)(2 * fd.minx);
+      total = l0 + l1 + l2;
+    }
+    // block exclusive scan of the candidate counts
+    int inc = total;
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += v;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += s_warp[w];
+    s_off[threadIdx.x] = woff + inc - total;
+    if (threadIdx.x == kPC - 1) s_off[kPC] = woff + inc;
+    __syncthreads();
+    const int P = s_off[kPC];
+    // ---- phase 2: one candidate test per thread and iteration
+    int nh = 0;
+    for (int pp = threadIdx.x; pp < P; pp += kPC) {
+      int lo = 0, hi = kPC;  // largest i with s_off[i] <= pp
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= pp) lo = mid; else hi = mid;
+      }
+      const int i = lo, k = pp - s_off[i];
+      const int l0 = s_l0[i], l01 = s_l01[i];
+      const int q = k < l0 ? s_qs[0][i] + k : (k < l01 ? s_qs[1][i] + (k - l0) : s_qs[2][i] + (k - l01));
+      const int4 ot = srt[q];
+      const int4 me = s_me[i];
+      const int a = me.z;
+      if (ot.z == a) continue;
+      if (fl_changed(ot.w) && ot.z < a) continue;  // that agent owns the pair
+      ++tests;
+      if (!within(ot.x - me.x, ot.y - me.y, p)) continue;
+      const FloorDev& fd = p.floors[fl_floor(me.w)];
+      if (!loc_rule_ordered(fd, a, fl_loc(me.w), ot.z, fl_loc(ot.w))) continue;
+      const uint32_t run = 1u + (uint32_t)min(fl_stay(me.w), fl_stay(ot.w));
+      hits += run;
+      ++runs;
+      if (buffered && nh < kHitSlots) {
+        ContactRec r;
+        r.a1 = (uint32_t)min(a, ot.z); r.a2 = (uint32_t)max(a, ot.z);
+        r.t_run = (t & 0xffffffu) | ((run - 1u) << 24);
+        r.bucket = ((s_hb[i] + (uint32_t)(me.y + ot.y) * (uint32_t)fd.hist_w + (uint32_t)(me.x + ot.x)) & 0x3fffffffu) | 0x40000000u;
+        mine[nh++] = r;
+      } else {
+        on_contact(p, t, me, ot, run, false, sub, true);
       }
     }
     if (buffered) {
@@ -770,10 +812,10 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
         int v = __shfl_up_sync(0xffffffffu, off, d);
         if (lane >= d) off += v;
       }
-      const int total = __shfl_sync(0xffffffffu, off, 31);
-      if (total > 0) {
+      const int wtotal = __shfl_sync(0xffffffffu, off, 31);
+      if (wtotal > 0) {
         unsigned long long wbase = 0;
-        if (lane == 31) wbase = atomicAdd(&p.ctr->cbuf_count[sub * kCounterStride], (unsigned long long)total);
+        if (lane == 31) wbase = atomicAdd(&p.ctr->cbuf_count[sub * kCounterStride], (unsigned long long)wtotal);
         wbase = __shfl_sync(0xffffffffu, wbase, 31) + (unsigned long long)(off - nh);
         for (int j = 0; j < nh; ++j) {
           if (wbase + j < p.cbuf_sub_cap) {
@@ -789,6 +831,7 @@ __global__ void __launch_bounds__(256) k_pairs_changed(Params p, int t_begin, in
         }
       }
     }
+    __syncthreads();  // the batch's shared arrays are reused
   }
   for (int d = 16; d > 0; d >>= 1) {
     tests += __shfl_down_sync(0xffffffffu, tests, d);
