@@ -116,7 +116,7 @@ struct DevCounters {
   unsigned long long stats[6];
   unsigned long long contact_runs;
   unsigned long long pad[2];
-  unsigned long long cbuf_count[kSubBuffers * kCounterStride];
+  unsigned long long cbuf_count[2][kSubBuffers * kCounterStride];  // one set per contact buffer
   unsigned long long pair_used_sub[kSubBuffers * kCounterStride];  // spread: inserts are frequent
 };
 
@@ -144,6 +144,7 @@ struct Params {
   unsigned long long log_cap;
   ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
   unsigned long long cbuf_sub_cap;
+  unsigned long long* cbuf_count;  // its kSubBuffers counters (stride kCounterStride)
   uint32_t* chg_list;   // [S][N] located agents whose state may differ from the step before
   uint32_t* chg_count;  // [S] x 32 (one counter per 128 bytes); NULL = lists not kept
   DevCounters* ctr;
@@ -578,7 +579,7 @@ __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const in
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long base = 0;
     if (g.thread_rank() == 0)
-      base = atomicAdd(&p.ctr->cbuf_count[sub * kCounterStride], (unsigned long long)g.size());
+      base = atomicAdd(&p.cbuf_count[sub * kCounterStride], (unsigned long long)g.size());
     base = g.shfl(base, 0) + g.thread_rank();
     if (base < p.cbuf_sub_cap) {
       ContactRec r;
@@ -815,7 +816,7 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
       const int wtotal = __shfl_sync(0xffffffffu, off, 31);
       if (wtotal > 0) {
         unsigned long long wbase = 0;
-        if (lane == 31) wbase = atomicAdd(&p.ctr->cbuf_count[sub * kCounterStride], (unsigned long long)wtotal);
+        if (lane == 31) wbase = atomicAdd(&p.cbuf_count[sub * kCounterStride], (unsigned long long)wtotal);
         wbase = __shfl_sync(0xffffffffu, wbase, 31) + (unsigned long long)(off - nh);
         for (int j = 0; j < nh; ++j) {
           if (wbase + j < p.cbuf_sub_cap) {
@@ -854,7 +855,7 @@ constexpr int kAccBlocksPerSub = 24;
 
 __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
   const int sub = blockIdx.x % kSubBuffers, part = blockIdx.x / kSubBuffers;
-  const unsigned long long n = min(p.ctr->cbuf_count[sub * kCounterStride], p.cbuf_sub_cap);
+  const unsigned long long n = min(p.cbuf_count[sub * kCounterStride], p.cbuf_sub_cap);
   const ContactRec* buf = p.cbuf + (unsigned long long)sub * p.cbuf_sub_cap;
   const unsigned long long stride = (unsigned long long)kAccBlocksPerSub * blockDim.x;
   for (unsigned long long i = (unsigned long long)part * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -879,8 +880,8 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
   }
 }
 
-__global__ void k_reset_cbuf(DevCounters* ctr) {
-  if (threadIdx.x < kSubBuffers) ctr->cbuf_count[threadIdx.x * kCounterStride] = 0ULL;
+__global__ void k_reset_cbuf(unsigned long long* cbuf_count) {
+  if (threadIdx.x < kSubBuffers) cbuf_count[threadIdx.x * kCounterStride] = 0ULL;
 }
 
 // The integer distance threshold must agree with the float64 predicate on THIS device.
@@ -1154,7 +1155,12 @@ struct citam_engine {
   bool have_itin = false;
 
   int S = 0;  // chunk capacity in steps
-  int4* rec = nullptr;
+  int4* rec = nullptr;  // the current one of rec_buf
+  int4* rec_buf[2] = {nullptr, nullptr};
+  int cur = 0;  // buffer set of the chunk being built (records + contact buffer are double-buffered)
+  cudaStream_t stream2 = nullptr;  // k_accumulate of chunk i runs here while chunk i+1 is built on `stream`
+  cudaEvent_t ev_built[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr};
+  bool applied_pending[2] = {false, false};
   uint32_t* cells = nullptr;
   int4* sorted = nullptr;
 
@@ -1168,7 +1174,8 @@ struct citam_engine {
   unsigned long long coord_cap = 0;
   citam_contact* log = nullptr;
   unsigned long long log_cap = 0;
-  ContactRec* cbuf = nullptr;
+  ContactRec* cbuf = nullptr;  // the current one of cbuf_buf
+  ContactRec* cbuf_buf[2] = {nullptr, nullptr};
   unsigned long long cbuf_cap = 0;
   uint32_t *chg_list = nullptr, *chg_count = nullptr, *part_sums = nullptr;
   unsigned long long* agent_dur = nullptr;
@@ -1214,22 +1221,45 @@ static unsigned long long next_pow2(unsigned long long v) {
 struct Timed {
   citam_engine* e;
   int kind;
+  cudaStream_t s;
   cudaEvent_t a = nullptr, b = nullptr;
-  Timed(citam_engine* e_, int k) : e(e_), kind(k) {
+  Timed(citam_engine* e_, int k, cudaStream_t s_ = nullptr, bool use_s = false) : e(e_), kind(k), s(use_s ? s_ : e_->stream) {
     e->launches++;
     if (e->timing) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, e->stream);
+      cudaEventRecord(a, s);
     }
   }
   ~Timed() {
     if (e->timing) {
-      cudaEventRecord(b, e->stream);
+      cudaEventRecord(b, s);
       e->evs.push_back({a, b, kind});
     }
   }
 };
+
+// Start building a chunk: take the other buffer set, once the accumulation that last read it is done.
+static int begin_chunk(citam_engine* e) {
+  e->cur ^= 1;
+  e->rec = e->rec_buf[e->cur];
+  e->cbuf = e->cbuf_buf[e->cur];
+  if (e->applied_pending[e->cur]) {
+    CK(cudaStreamWaitEvent(e->stream, e->ev_applied[e->cur], 0));
+    e->applied_pending[e->cur] = false;
+  }
+  return CITAM_OK;
+}
+
+// Everything enqueued on the side stream happens before whatever follows on the engine's stream.
+static int join_side_stream(citam_engine* e) {
+  for (int b = 0; b < 2; ++b)
+    if (e->applied_pending[b]) {
+      CK(cudaStreamWaitEvent(e->stream, e->ev_applied[b], 0));
+      e->applied_pending[b] = false;
+    }
+  return CITAM_OK;
+}
 
 static void drain_timings(citam_engine* e) {
   for (auto& v : e->evs) {
@@ -1259,6 +1289,7 @@ static Params make_params(citam_engine* e) {
   p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist; p.range_begin = e->range_begin;
   p.log = e->log; p.log_cap = e->log_cap;
   p.cbuf = (e->log_cap || !e->hist) ? nullptr : e->cbuf; p.cbuf_sub_cap = e->cbuf_cap / kSubBuffers;
+  p.cbuf_count = e->ctr_d->cbuf_count[e->cur];
   const bool agg = e->log_cap == 0;  // run aggregation (off when every contact-step is logged)
   p.chg_list = agg ? e->chg_list : nullptr; p.chg_count = agg ? e->chg_count : nullptr;
   p.ctr = e->ctr_d;
@@ -1266,8 +1297,12 @@ static Params make_params(citam_engine* e) {
 }
 
 static void free_chunk(citam_engine* e) {
-  cudaFree(e->rec); cudaFree(e->cells);
-  cudaFree(e->sorted); cudaFree(e->cbuf); cudaFree(e->chg_list); cudaFree(e->chg_count); cudaFree(e->part_sums);
+  cudaStreamSynchronize(e->stream);
+  if (e->stream2) cudaStreamSynchronize(e->stream2);
+  e->applied_pending[0] = e->applied_pending[1] = false;
+  for (int b = 0; b < 2; ++b) { cudaFree(e->rec_buf[b]); cudaFree(e->cbuf_buf[b]); e->rec_buf[b] = nullptr; e->cbuf_buf[b] = nullptr; }
+  cudaFree(e->cells);
+  cudaFree(e->sorted); cudaFree(e->chg_list); cudaFree(e->chg_count); cudaFree(e->part_sums);
   e->chg_list = e->chg_count = e->part_sums = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
@@ -1317,14 +1352,16 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   free_chunk(e);
   int S = want_steps;
   size_t n = (size_t)e->N;
-  CK(cudaMalloc(&e->rec, sizeof(int4) * n * (S + 1)));
+  for (int b = 0; b < 2; ++b) CK(cudaMalloc(&e->rec_buf[b], sizeof(int4) * n * (S + 1)));
+  e->rec = e->rec_buf[e->cur];
   CK(cudaMalloc(&e->cells, sizeof(uint32_t) * (size_t)e->cells_stride * S));
   CK(cudaMalloc(&e->sorted, sizeof(int4) * n * S));
   // contact buffer: one record per detected contact run of a chunk (overflow falls back to
   // inline accumulation, so the size is a performance knob, not a limit)
-  e->cbuf_cap = std::min<unsigned long long>(256ULL << 20, std::max<unsigned long long>(1ULL << 16, 4ULL * n * S));
+  e->cbuf_cap = std::min<unsigned long long>(128ULL << 20, std::max<unsigned long long>(1ULL << 16, 2ULL * n * S));
   e->cbuf_cap = (e->cbuf_cap + kSubBuffers - 1) / kSubBuffers * kSubBuffers;
-  CK(cudaMalloc(&e->cbuf, sizeof(ContactRec) * e->cbuf_cap));
+  for (int b = 0; b < 2; ++b) CK(cudaMalloc(&e->cbuf_buf[b], sizeof(ContactRec) * e->cbuf_cap));
+  e->cbuf = e->cbuf_buf[e->cur];
   CK(cudaMalloc(&e->chg_list, sizeof(uint32_t) * n * S));
   CK(cudaMalloc(&e->chg_count, sizeof(uint32_t) * 32 * S));
   CK(cudaMalloc(&e->part_sums, sizeof(uint32_t) * kMaxScanParts * S));
@@ -1381,9 +1418,16 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     }
   }
   if (p.cbuf != nullptr) {
-    Timed tm(e, CITAM_K_ACCUMULATE);
-    k_accumulate<<<kSubBuffers * kAccBlocksPerSub, 256, 0, e->stream>>>(p, t_begin);
-    k_reset_cbuf<<<1, kSubBuffers, 0, e->stream>>>(e->ctr_d);
+    // the contact buffer is applied on the side stream, overlapping the next chunk's build
+    CK(cudaEventRecord(e->ev_built[e->cur], e->stream));
+    CK(cudaStreamWaitEvent(e->stream2, e->ev_built[e->cur], 0));
+    {
+      Timed tm(e, CITAM_K_ACCUMULATE, e->stream2, true);
+      k_accumulate<<<kSubBuffers * kAccBlocksPerSub, 256, 0, e->stream2>>>(p, t_begin);
+      k_reset_cbuf<<<1, kSubBuffers, 0, e->stream2>>>(p.cbuf_count);
+    }
+    CK(cudaEventRecord(e->ev_applied[e->cur], e->stream2));
+    e->applied_pending[e->cur] = true;
   }
   CK(cudaGetLastError());
   return CITAM_OK;
@@ -1447,6 +1491,11 @@ int citam_create(const citam_config* cfg, citam_engine** out) {
   CK(cudaMalloc(&e->ctr_d, sizeof(DevCounters)));
   CK(cudaMalloc(&e->prev, sizeof(int4) * n));
   CK(cudaMalloc(&e->states_d, sizeof(citam_agent_state) * n));
+  CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaEventCreateWithFlags(&e->ev_built[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_applied[b], cudaEventDisableTiming));
+  }
   {
     int* bad_d = nullptr;
     int bad = 1;
@@ -1464,8 +1513,11 @@ void citam_destroy(citam_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  if (e->stream2) cudaStreamSynchronize(e->stream2);
   drain_timings(e);
   free_chunk(e);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
+  for (int b = 0; b < 2; ++b) { if (e->ev_built[b]) cudaEventDestroy(e->ev_built[b]); if (e->ev_applied[b]) cudaEventDestroy(e->ev_applied[b]); }
   for (auto p : e->lut_d) cudaFree(p);
   for (auto p : e->adj_d) cudaFree(p);
   cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->pairs);
@@ -1612,6 +1664,10 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
 // Library-chosen pair capacity: double the table once it is half full (checked between chunks).
 static int maybe_grow_pairs(citam_engine* e) {
   if (!e->pair_auto) return CITAM_OK;
+  {  // the table is about to be read (and perhaps replaced): no accumulation may be in flight
+    int rcj = join_side_stream(e);
+    if (rcj) return rcj;
+  }
   DevCounters c;
   CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1654,6 +1710,8 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
   if (rc) return rc;
   e->range_begin = t_begin;
   for (int tb = t_begin; tb < t_end; tb += S) {
+    rc = begin_chunk(e);
+    if (rc) return rc;
     Params p = make_params(e);
     int steps = std::min(S, t_end - tb);
     int rows = steps + 1;  // + halo row for step tb-1
@@ -1676,7 +1734,7 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     if (rc) return rc;
   }
   e->prev_step = LLONG_MIN;
-  return CITAM_OK;
+  return join_side_stream(e);
 }
 
 int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* states) {
@@ -1687,6 +1745,8 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   if (rc) return rc;
   size_t n = (size_t)e->N;
   int g = (e->N + 255) / 256;
+  rc = begin_chunk(e);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(e->states_d, states, sizeof(citam_agent_state) * n, cudaMemcpyHostToDevice, e->stream));
   if (e->prev_step == (long long)step - 1) {
     CK(cudaMemcpyAsync(e->rec, e->prev, sizeof(int4) * n, cudaMemcpyDeviceToDevice, e->stream));
@@ -1709,6 +1769,8 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   CK(cudaMemcpyAsync(e->prev, e->rec + n, sizeof(int4) * n, cudaMemcpyDeviceToDevice, e->stream));
   e->prev_step = step;
   e->agent_steps += e->N;
+  rc = join_side_stream(e);
+  if (rc) return rc;
   rc = maybe_grow_pairs(e);
   if (rc) return rc;
   return check_overflow(e);
