@@ -1393,6 +1393,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     parts = (n4 + part_len4 - 1) / part_len4;
     k_scan<<<dim3(parts, rows), kScanThreads, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
                                                               e->part_sums);
+    if (parts > 1) e->launches++;
     if (parts > 1)
       k_scan_add<<<dim3(parts - 1, rows), 256, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
                                                                e->part_sums);
@@ -1402,6 +1403,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     dim3 g((e->N + 255) / 256, rows);
     k_scatter<<<g, 256, 0, e->stream>>>(p, rows);
     if (p.chg_count != nullptr && rows > 1) {
+      e->launches++;
       dim3 g3((unsigned)std::min(296, std::max(1, (e->N + 255) / 256)), rows - 1);
       k_select_changed<<<g3, 256, 0, e->stream>>>(p, rows);
     }
@@ -1413,6 +1415,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     dim3 g((e->N + 255) / 256, agg ? 1 : rows);
     k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0);
     if (agg && rows > 1) {
+      e->launches++;
       dim3 g2((unsigned)std::min(592, std::max(1, (e->N + 255) / 256)), rows - 1);
       k_pairs_changed<<<g2, 256, 0, e->stream>>>(p, t_begin, rows);
     }
@@ -1425,6 +1428,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
       Timed tm(e, CITAM_K_ACCUMULATE, e->stream2, true);
       k_accumulate<<<kSubBuffers * kAccBlocksPerSub, 256, 0, e->stream2>>>(p, t_begin);
       k_reset_cbuf<<<1, kSubBuffers, 0, e->stream2>>>(p.cbuf_count);
+      e->launches++;
     }
     CK(cudaEventRecord(e->ev_applied[e->cur], e->stream2));
     e->applied_pending[e->cur] = true;
