@@ -298,6 +298,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
