@@ -201,3 +201,34 @@ def test_kat_per_coordinate_histogram():
     ev.add_contact(a1, a2, 3, (5, 5))
     assert port.contacts_per_coordinates(ev.contact_data, 0) == {(1, 1): 2, (2, 1): 1}
     assert port.contacts_per_coordinates(ev.contact_data, 1) == {(5, 5): 1}
+
+
+def test_unmodified_reference_still_reproduces_the_two_floor_fixture(tmp_path):
+    """Build container only: re-run the real reference (oracle/refload.py) on the two-floor case and
+    compare with the committed fixture, so the golden files cannot drift from the generator."""
+    from oracle import refload
+
+    if not refload.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import subprocess
+    import sys
+
+    # run the generator's two-floor case in a scratch copy of tests/golden
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, os\n"
+        "sys.path.insert(0, %r)\n"
+        "import oracle.make_golden as g\n"
+        "g.GOLD = %r\n"
+        "os.makedirs(g.GOLD, exist_ok=True)\n"
+        "g.case_twofloor()\n" % (root, str(tmp_path))
+    )
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    case = load_case("twofloor")
+    import gzip
+
+    for fn in ["pair_contact.csv", "contact_dist_per_agent.csv", "statistics.json", "trajectory.txt", "floor_0/contacts.txt",
+               "floor_1/contact_dist_per_coord.csv"]:
+        with gzip.open(os.path.join(str(tmp_path), "twofloor", "expected", fn + ".gz"), "rb") as f:
+            assert f.read() == expected(case, fn), fn
