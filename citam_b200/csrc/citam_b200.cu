@@ -17,8 +17,8 @@
 //                 row above) with the reference's float64 predicate, then accumulation: one
 //                 64-bit atomic into the 16-byte per-pair entry (duration | events<<32), one
 //                 64-bit reduction into the dense per-coordinate histogram, and the optional
-//                 contact log.  Per-agent contact seconds are derived from the pair table at
-//                 export time (sum over the agent's pairs), not counted per contact.
+//                 contact log; both agents' contact seconds (N x 8 bytes, L2-resident) get one
+//                 reduction each per table update.
 // All of this is HBM/L2-bound integer work; there is no GEMM in the path.
 
 #include "../../include/citam_b200.h"
@@ -145,6 +145,7 @@ struct Params {
   ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
   unsigned long long cbuf_sub_cap;
   unsigned long long* cbuf_count;  // its kSubBuffers counters (stride kCounterStride)
+  unsigned long long* agent_dur;   // [N] contact-steps per agent
   uint32_t* chg_list;   // [S][N] located agents whose state may differ from the step before
   uint32_t* chg_count;  // [S] x 32 (one counter per 128 bytes); NULL = lists not kept
   DevCounters* ctr;
@@ -493,7 +494,7 @@ __device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigne
 }
 
 __device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
-                                           unsigned long long add_dur, unsigned long long add_nev);
+                                           unsigned long long add_dur, unsigned long long add_nev, uint32_t a1, uint32_t a2);
 // add_dur contact-steps and add_nev events; `first` (a step, or NO_STEP) lowers the pair's
 // first-contact step.  The first contact of a pair is always an event start, so callers pass a
 // step only for event starts and for the first step of a run range.
@@ -503,7 +504,7 @@ __device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32
   unsigned long long old;
   unsigned long long h = pair_slot(p, key, &old);
   if (h == ~0ULL) return;
-  pair_apply(p, h, old, first, add_dur, add_nev);
+  pair_apply(p, h, old, first, add_dur, add_nev, a1, a2);
 }
 
 __device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx, int sy, unsigned long long add) {
@@ -549,9 +550,13 @@ __device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, u
   return contact_eval(p, p.rec[prow_off + a1], p.rec[prow_off + a2]);
 }
 
-// pair_upsert split in two so that a caller can put independent loads between probe and update
+// pair_upsert split in two so that a caller can put independent loads between probe and update.
+// Also adds the contact-steps to both agents' counters (close_contacts_calculator.py:221-224): the
+// counter array is N x 8 bytes, L2-resident, so these two reductions cost no DRAM access.
 __device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
-                                           unsigned long long add_dur, unsigned long long add_nev) {
+                                           unsigned long long add_dur, unsigned long long add_nev, uint32_t a1, uint32_t a2) {
+  atomicAdd(&p.agent_dur[a1], add_dur);
+  atomicAdd(&p.agent_dur[a2], add_dur);
   unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
   for (;;) {
     unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
@@ -876,7 +881,7 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
     if (h == ~0ULL) continue;
     if (late) was = contact_eval(p, r1, r2);
     uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
-    pair_apply(p, h, acc, first, run, was ? 0u : 1u);
+    pair_apply(p, h, acc, first, run, was ? 0u : 1u, r.a1, r.a2);
   }
 }
 
@@ -1039,18 +1044,6 @@ __global__ void k_hist_compact(const unsigned long long* hist, long long n, int 
   r.reserved = 0;
   r.count = c;
   out[base] = r;
-}
-
-// per-agent contact seconds = sum of the durations of the agent's pairs
-// (close_contacts_calculator.py:221-224 increments both agents once per contact-step)
-__global__ void k_agent_durations(const PairEntry* tab, unsigned long long cap, unsigned long long* agent_dur) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cap) return;
-  PairEntry e = tab[i];
-  if (e.key == 0ULL) return;
-  unsigned long long d = ACC_DUR(e.acc);
-  atomicAdd(&agent_dur[(uint32_t)(e.key >> 32)], d);
-  atomicAdd(&agent_dur[(uint32_t)(e.key & 0xffffffffu)], d);
 }
 
 __global__ void k_rehash_pairs(Params p, const PairEntry* old_tab, unsigned long long old_cap) {
@@ -1290,6 +1283,7 @@ static Params make_params(citam_engine* e) {
   p.log = e->log; p.log_cap = e->log_cap;
   p.cbuf = (e->log_cap || !e->hist) ? nullptr : e->cbuf; p.cbuf_sub_cap = e->cbuf_cap / kSubBuffers;
   p.cbuf_count = e->ctr_d->cbuf_count[e->cur];
+  p.agent_dur = e->agent_dur;
   const bool agg = e->log_cap == 0;  // run aggregation (off when every contact-step is logged)
   p.chg_list = agg ? e->chg_list : nullptr; p.chg_count = agg ? e->chg_count : nullptr;
   p.ctr = e->ctr_d;
@@ -1543,6 +1537,7 @@ int citam_reset(citam_engine* e) {
   CK(cudaMemsetAsync(e->pairs, 0, sizeof(PairEntry) * e->pair_cap, e->stream));
   CK(cudaMemsetAsync(e->coords, 0, sizeof(CoordEntry) * e->coord_cap, e->stream));
   if (e->hist) CK(cudaMemsetAsync(e->hist, 0, sizeof(unsigned long long) * (size_t)e->hist_total, e->stream));
+  CK(cudaMemsetAsync(e->agent_dur, 0, sizeof(unsigned long long) * (size_t)e->N, e->stream));
   CK(cudaMemsetAsync(e->ctr_d, 0, sizeof(DevCounters), e->stream));
   e->prev_step = LLONG_MIN;
   e->agent_steps = 0;
@@ -1954,22 +1949,10 @@ int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, ui
   return CITAM_OK;
 }
 
-static int compute_agent_durations(citam_engine* e) {
-  CK(cudaMemsetAsync(e->agent_dur, 0, sizeof(unsigned long long) * (size_t)e->N, e->stream));
-  {
-    Timed tm(e, CITAM_K_FINALIZE);
-    k_agent_durations<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, e->agent_dur);
-  }
-  CK(cudaGetLastError());
-  return CITAM_OK;
-}
-
 int citam_export_agent_durations(citam_engine* e, uint64_t* out) {
   if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->device));
   int rc = check_overflow(e);
-  if (rc) return rc;
-  rc = compute_agent_durations(e);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, e->agent_dur, sizeof(uint64_t) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -2041,8 +2024,6 @@ int citam_get_timings(citam_engine* e, citam_timings* out) {
 int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements) {
   if (!e || !ptr || !n_elements) return fail(CITAM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->device));
-  int rc = compute_agent_durations(e);
-  if (rc) return rc;
   CK(cudaStreamSynchronize(e->stream));
   *ptr = e->agent_dur;
   *n_elements = (uint64_t)e->N;

@@ -214,8 +214,8 @@ int citam_get_counters(citam_engine* e, citam_counters* out);
 int citam_get_timings(citam_engine* e, citam_timings* out);
 
 /* Device views for the multi-GPU reduction (torch.distributed/NCCL all-reduce
- * straight on engine memory): per-agent contact seconds, uint64 [n_agents],
- * recomputed from the pair table by this call. */
+ * on engine memory): per-agent contact seconds, uint64 [n_agents].  The pointer is the live
+ * counter array: reduce into a copy if the engine goes on accumulating or merging. */
 int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements);
 /* Merge pair / coordinate records exported by another engine (other rank). */
 int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n);

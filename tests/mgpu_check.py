@@ -27,13 +27,13 @@ def main():
     eng.load_geometry(fac.geometry)
     eng.load_segments(seg_off, segs)
     run = D.ShardedRun(eng, p["total_timesteps"], block=173).run()
-    # device view of the per-agent seconds, all-reduced in place over NCCL
+    # device view of the per-agent seconds, all-reduced over NCCL
     ptr, n = eng.agent_durations_device()
 
     class Holder:
         __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
 
-    t = torch.as_tensor(Holder(), device="cuda")
+    t = torch.as_tensor(Holder(), device="cuda").clone()  # the engine's own counters stay per-rank
     dist.all_reduce(t)
     dur_nccl = t.cpu().numpy().tolist()
     pairs, coords, dur = run.reduce(into_engine=True)
@@ -45,7 +45,7 @@ def main():
         assert got[0] == want[0], "pairs differ"
         assert got[1] == want[1], "coords differ"
         assert got[2] == want[2], "durations differ"
-        assert dur_nccl == want[2], "in-place NCCL all-reduce differs"
+        assert dur_nccl == want[2], "NCCL all-reduce of the device counters differs"
         assert dur.tolist() == want[2]
         print("mgpu ok: world", dist.get_world_size(), "pairs", len(got[0]))
     dist.barrier()
