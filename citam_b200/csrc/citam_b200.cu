@@ -7,19 +7,23 @@
 //   CloseContactsCalculator.run               citam/engine/calculators/close_contacts_calculator.py:64-231
 //   ContactEvents.add_contact / statistics    citam/engine/calculators/contacts.py:92-294
 //
-// Pipeline per chunk of S time steps (all steps of a chunk are processed by one
-// launch each; accumulators are commutative so steps are independent):
-//   k_expand_bin  itinerary segments -> per-step SoA state rows (x, y, floor|loc) and the
-//                 uniform-grid histogram (one atomic per located agent returns its rank)
-//   k_scan        per-step exclusive scan of the cell histogram, staged in shared memory
-//   k_scatter     counting-sort scatter into cell order (16-byte records)
-//   k_pairs       half-neighbourhood pair test (own cell tail + right cell + 3 cells of the
-//                 row above) with the reference's float64 predicate, then accumulation: one
-//                 64-bit atomic into the 16-byte per-pair entry (duration | events<<32), one
-//                 64-bit reduction into the dense per-coordinate histogram, and the optional
-//                 contact log; both agents' contact seconds (N x 8 bytes, L2-resident) get one
-//                 reduction each per table update.
-// All of this is HBM/L2-bound integer work; there is no GEMM in the path.
+// Pipeline per chunk of S <= 256 time steps (one launch per stage covers all steps of the chunk;
+// every accumulator is commutative, so steps, chunks and time blocks are independent):
+//   k_expand_bin      itinerary segments -> per-step 16-byte records {x, y, state word, rank}; one
+//                     atomic per located agent returns its rank in its uniform-grid cell
+//   k_scan(+_add)     per-step exclusive scan of the cell histogram (rows x pieces CTAs)
+//   k_scatter         counting-sort scatter into cell order (16-byte records)
+//   k_select_changed  per step, the agents whose state may differ from the step before, in cell order
+//   k_pairs           first step of the chunk: every located agent against its half neighbourhood
+//                     (own cell tail, right cell, 3 cells above), candidate window in shared memory
+//   k_pairs_changed   other steps: only changed agents, 3x3 neighbourhood, tests flattened over a
+//                     256-agent batch; a contact of two unchanged agents is inside a run that an
+//                     earlier step added in one piece (stationary-run aggregation)
+//   k_accumulate      (side stream, overlaps the next chunk) one contact-run record per thread:
+//                     16-byte pair-table slot probe + one CAS, one 64-bit reduction into the dense
+//                     per-coordinate histogram, two reductions into the L2-resident per-agent counters
+// The distance predicate is the reference's float64 sqrt(dx^2+dy^2) < D as an exact integer
+// threshold (find_s_max).  All of this is HBM/L2-bound integer work; there is no GEMM in the path.
 
 #include "../../include/citam_b200.h"
 
@@ -445,11 +449,7 @@ __device__ __forceinline__ bool loc_rule_ordered(const FloorDev& fd, int ida, in
 // `< contact_distance` of np.argwhere (close_contacts_calculator.py:169-171).  dx, dy are exact
 // integers, so s = dx^2+dy^2 is exact, and s -> sqrt_rn((double)s) is monotone: the predicate
 // holds exactly for s <= s_max, where the host found s_max with the same IEEE operations
-// (find_s_max; checked against the float64 form by within_f64 in the tests' LUT/step paths).
-__device__ __forceinline__ bool within_f64(int dx, int dy, double D) {
-  long long s = (long long)dx * dx + (long long)dy * dy;
-  return __dsqrt_rn((double)s) < D;
-}
+// (find_s_max) and citam_create checked it on the device against __dsqrt_rn (k_check_s_max).
 __device__ __forceinline__ bool within(int dx, int dy, const Params& p) {
   long long s = (long long)dx * dx + (long long)dy * dy;
   return s <= p.s_max;
