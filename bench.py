@@ -388,7 +388,7 @@ def run_b200(args):
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
         roof = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": profiled_traffic(dom), "traffic_source": "profiles/r1_ncu_full_top_kernels.csv (one launch, 64 steps x 1e6 agents)",
+            "traffic": profiled_traffic(dom) if args.workload == "config3" and not args.agents else None, "traffic_source": "profiles/r1_ncu_full_top_kernels.csv (one launch, 64 steps x 1e6 agents)",
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
             "algorithmic_bytes_rule": "k_accumulate: 64 B x contact-steps; expand/scatter/pairs: 12 B x agent-steps; whole step: both",
