@@ -168,7 +168,10 @@ def build_workload(args):
 
 
 def auto_block(p):
-    # ~2.4e8 agent-steps per bench step, at least 32 simulation steps
+    # ~2.4e8 agent-steps per bench step, at least 32 simulation steps; the dense-crowding shape has
+    # ~50 contact-steps per agent-step, so its blocks are kept short
+    if p.get("social", 0) > 0.8:
+        return 48
     return int(max(32, min(960, 240_000_000 // max(1, p["n_agents"]))))
 
 
