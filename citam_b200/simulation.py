@@ -52,10 +52,17 @@ class Simulation:
         else:
             raise ValueError("Invalid calculator. Must be an instance of Calculator")
         if scheduler is None:
-            raise ValueError(
-                "No scheduler provided. Itinerary generation (the reference's OfficeScheduler) is outside "
-                "this package: pass the reference's scheduler or a PrecomputedScheduler / SegmentScheduler."
-            )
+            # upstream defaults to its OfficeScheduler (simulation.py:133-141); itinerary generation is
+            # not rebuilt here, so the default exists only where the upstream package is installed
+            try:
+                from citam.engine.schedulers.office_scheduler import OfficeScheduler
+            except ImportError:
+                raise ValueError(
+                    "No scheduler provided. Itinerary generation (the reference's OfficeScheduler) is outside "
+                    "this package: pass the reference's scheduler or a PrecomputedScheduler / SegmentScheduler."
+                )
+            LOG.info("No scheduler provided. Defaulting to office scheduler.")
+            scheduler = OfficeScheduler(facility, total_timesteps)
         if not isinstance(scheduler, Scheduler) and not (hasattr(scheduler, "run") and hasattr(scheduler, "save_to_files")):
             raise ValueError("Invalid scheduler. Must be an instance of Scheduler")
         self.scheduler = scheduler
