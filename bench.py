@@ -58,6 +58,7 @@ def parse_args():
 
 
 _T0 = time.time()
+_OUT = sys.stdout  # replaced in __main__ by a private handle on the real stdout
 
 
 def log(*a):
@@ -268,7 +269,7 @@ def run_reference(args):
         "note": "oracle/grid_oracle.c (grid restatement of the reference path, OpenMP time blocks); the upstream "
                 "reference itself is single-threaded O(N^2) Python/scipy and cannot hold this N",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def workload_config(args, p, block):
@@ -302,8 +303,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -483,13 +482,17 @@ def run_b200(args):
             "pair_tests_per_s": pair_tests / (ms * 1e-3), "table_updates_per_contact_step": runs / max(1, contacts),
             "final_reduce_ms": final_reduce_ms,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr,
+    # so that library banners (e.g. NCCL's version line) cannot land in front of the result
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
