@@ -183,7 +183,13 @@ def cpu_oracle(fac, seg_off, segs, p, D):
     from citam_b200 import facility as F
     from oracle import grid
 
-    threads = grid.max_threads()
+    # every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the oracle's time-block
+    # threads are requested explicitly, so that setting does not bind it)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    threads = max(grid.max_threads(), cores)
     floors = []
     cache = {}
     for fg in fac.geometry["floors"]:
