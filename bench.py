@@ -241,7 +241,7 @@ def time_faithful_port(fac, seg_off, segs, p, D, n_sub=1500, steps=12):
         sim.step()
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port (reference formulation, pdist O(N^2))",
-            "sample": "%d agents x %d steps at mid-day (%.1f s)" % (n, steps, dt)}
+            "sample": "the first %d agents x %d steps in the middle of the first shift (%.2f s)" % (n, steps, dt)}
 
 
 def run_reference(args):
