@@ -134,6 +134,8 @@ struct Params {
   const FloorDev* floors;
   const int4* segs;  // {t0 | floor<<24, x0, y0, dx&0xffff | dy<<16}
   const long long* seg_off;
+  const int2* window;  // per agent {first step in the facility, first step of a final stay outside every space}
+                       // (INT_MAX when there is none); NULL = not available
   int4* rec;        // [(S+1)][N] {x, y, state word, rank in cell}; row 0 = halo step t_begin-1
   uint32_t* cells;  // [S][cells_stride]
   int4* sorted;     // [S][N] {x, y, agent, state word} in cell order
@@ -204,6 +206,23 @@ __device__ __forceinline__ int cell_of(const FloorDev& fd, int cell, int x, int 
   return fd.cell_base + cy * fd.ncx + cx;
 }
 
+// Per agent, the steps at which it can matter to the loop: before `x` it is not in the facility;
+// from `y` on it sits for ever at a point outside every space (the sticky tail of a finished
+// itinerary).  Outside [x - 1, y) the step kernels neither write nor read the agent's records.
+__global__ void k_agent_windows(Params p, int2* out) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.N) return;
+  long long sb = p.seg_off[a], se = p.seg_off[a + 1];
+  int2 w = make_int2(INT_MAX, INT_MAX);
+  if (se > sb) {
+    w.x = p.segs[sb].x & 0xffffff;
+    int4 last = p.segs[se - 1];
+    int f = (last.x >> 24) & 0xff;
+    if (last.w == 0 && (f >= p.F || lut_lookup(p.floors[f], last.y, last.z) < 0)) w.y = last.x & 0xffffff;
+  }
+  out[a] = w;
+}
+
 // --------------------------------------------------------------------------
 // K1a: itinerary expansion + grid histogram.
 // One thread walks one agent through kRowsPerThread consecutive steps: the segment cursor
@@ -215,6 +234,12 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= p.N) return;
   int r0 = blockIdx.y * kRowsPerThread;
+  int2 win = make_int2(INT_MIN, INT_MAX);
+  if (do_bin && p.window != nullptr) {
+    win = p.window[a];
+    // nothing of this thread's steps lies in [enter - 1, exit): no record is written (none is read)
+    if (win.x > t_first + min(r0 + kRowsPerThread, rows) || win.y <= t_first + r0) return;
+  }
   long long sb = p.seg_off[a], se = p.seg_off[a + 1];
   int t = t_first + r0;
   long long lo = sb, hi = se;  // first segment with t0 > t
@@ -240,6 +265,7 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
       next_t0 = (c + 1 < se) ? (__ldg(&p.segs[c + 1].x) & 0xffffff) : INT_MAX;
     }
     size_t o = (size_t)row * p.N + a;
+    if (t + 1 < win.x || t >= win.y) continue;  // outside the agent's window (see k_agent_windows)
     if (c < sb || t < 0) {
       p.rec[o] = make_int4(0, 0, pack_fl(-1, -1), 0);
       continue;
@@ -394,10 +420,15 @@ __global__ void __launch_bounds__(256) k_scan_add(uint32_t* cells, int stride, i
 // --------------------------------------------------------------------------
 // K3: counting-sort scatter into cell order.
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */) {
+__global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */, int t_begin) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   int row = blockIdx.y;
   if (a >= p.N || row >= rows) return;
+  if (p.window != nullptr) {  // 8 bytes instead of the 16-byte record for agents that are not around
+    const int2 win = p.window[a];
+    const int t = t_begin + row;
+    if (t < win.x || t >= win.y) return;
+  }
   int4 r = p.rec[(size_t)(row + 1) * p.N + a];
   int f = fl_floor(r.z), loc = fl_loc(r.z);
   if (f < 0 || loc < 0) return;
@@ -1145,6 +1176,9 @@ struct citam_engine {
   int64_t segs_cap = 0;
   long long* seg_off_d = nullptr;
   long long n_segs = 0;
+  int2* window_d = nullptr;  // k_agent_windows
+  bool window_dirty = true;
+  bool explicit_states = false;  // citam_step_states in progress: states come from the caller, no windows
   bool have_itin = false;
 
   int S = 0;  // chunk capacity in steps
@@ -1277,6 +1311,7 @@ static Params make_params(citam_engine* e) {
   Params p{};
   p.N = e->N; p.F = e->F; p.cell = e->cell; p.total_cells = e->total_cells; p.cells_stride = e->cells_stride;
   p.D = e->D; p.s_max = e->s_max; p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
+  p.window = (e->have_itin && !e->window_dirty && !e->explicit_states) ? e->window_d : nullptr;
   p.rec = e->rec; p.cells = e->cells;
   p.sorted = e->sorted; p.pairs = e->pairs; p.pair_mask = e->pair_cap - 1;
   p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist; p.range_begin = e->range_begin;
@@ -1340,6 +1375,7 @@ static int ensure_ready(citam_engine* e, int want_steps) {
     CK(cudaMemcpyAsync(e->floors_d, e->floors_h.data(), sizeof(FloorDev) * e->F, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->floors_dirty = false;
+    e->window_dirty = true;  // the final-stay test reads the location tables
     free_chunk(e);
   }
   if (e->S >= want_steps && e->rec) return CITAM_OK;
@@ -1395,7 +1431,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
   {
     Timed tm(e, CITAM_K_SCATTER);
     dim3 g((e->N + 255) / 256, rows);
-    k_scatter<<<g, 256, 0, e->stream>>>(p, rows);
+    k_scatter<<<g, 256, 0, e->stream>>>(p, rows, t_begin);
     if (p.chg_count != nullptr && rows > 1) {
       e->launches++;
       dim3 g3((unsigned)std::min(296, std::max(1, (e->N + 255) / 256)), rows - 1);
@@ -1518,7 +1554,7 @@ void citam_destroy(citam_engine* e) {
   for (int b = 0; b < 2; ++b) { if (e->ev_built[b]) cudaEventDestroy(e->ev_built[b]); if (e->ev_applied[b]) cudaEventDestroy(e->ev_applied[b]); }
   for (auto p : e->lut_d) cudaFree(p);
   for (auto p : e->adj_d) cudaFree(p);
-  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->pairs);
+  cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->window_d); cudaFree(e->pairs);
   cudaFree(e->coords); cudaFree(e->hist);
   cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->ctr_d);
   cudaFree(e->prev); cudaFree(e->states_d);
@@ -1657,6 +1693,7 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
   CK(cudaStreamSynchronize(e->stream));  // the caller's host buffers are free to change again
   e->n_segs = n_segs;
   e->have_itin = true;
+  e->window_dirty = true;
   return CITAM_OK;
 }
 
@@ -1707,6 +1744,16 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
   int S = pick_chunk(e, t_end - t_begin);
   rc = ensure_ready(e, S);
   if (rc) return rc;
+  if (e->window_dirty) {
+    if (!e->window_d) CK(cudaMalloc(&e->window_d, sizeof(int2) * (size_t)e->N));
+    Params p0 = make_params(e);
+    {
+      Timed tm(e, CITAM_K_MISC);
+      k_agent_windows<<<(e->N + 255) / 256, 256, 0, e->stream>>>(p0, e->window_d);
+    }
+    CK(cudaGetLastError());
+    e->window_dirty = false;
+  }
   e->range_begin = t_begin;
   for (int tb = t_begin; tb < t_end; tb += S) {
     rc = begin_chunk(e);
@@ -1746,6 +1793,7 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   int g = (e->N + 255) / 256;
   rc = begin_chunk(e);
   if (rc) return rc;
+  struct Flag { bool& f; Flag(bool& x) : f(x) { f = true; } ~Flag() { f = false; } } flag(e->explicit_states);
   CK(cudaMemcpyAsync(e->states_d, states, sizeof(citam_agent_state) * n, cudaMemcpyHostToDevice, e->stream));
   if (e->prev_step == (long long)step - 1) {
     CK(cudaMemcpyAsync(e->rec, e->prev, sizeof(int4) * n, cudaMemcpyDeviceToDevice, e->stream));
