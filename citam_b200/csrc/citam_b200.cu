@@ -589,6 +589,13 @@ __device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h
   atomicAdd(&p.agent_dur[a1], add_dur);
   atomicAdd(&p.agent_dur[a2], add_dur);
   unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
+  if (finv <= ACC_FIRST_INV(old)) {
+    // the first-contact field cannot move (it only grows, and ours is not larger): the update is a
+    // plain addition on the packed word -- one reduction, no round trip, no retry
+    if (ACC_DUR(old) + add_dur > 0xffffffULL || ACC_NEV(old) + add_nev > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
+    atomicAdd(&p.pairs[h].acc, add_dur | (add_nev << 24));
+    return;
+  }
   for (;;) {
     unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
     if (d > 0xffffffULL || n > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
