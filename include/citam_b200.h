@@ -18,6 +18,13 @@
  *
  * There is no CPU fallback: `citam_create` fails when no sm_100 device is
  * usable.
+ *
+ * Limits (checked; violations return CITAM_ERR_INVALID or CITAM_ERR_CAPACITY):
+ *   floors <= 63, spaces per floor <= 32767, steps < 2^24, |coordinates| < 2^26,
+ *   per-step stride of a segment within int16, contact-steps per pair < 2^24 and
+ *   events per pair < 2^16, steps_per_chunk <= 256.  Itinerary coordinates are
+ *   integers (the reference's navigation lattice); contact positions are their
+ *   midpoints, reported as (x1+x2, y1+y2).
  */
 #ifndef CITAM_B200_H
 #define CITAM_B200_H
