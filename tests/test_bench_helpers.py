@@ -1,0 +1,46 @@
+"""CPU: bench.py's host-side helpers and the replica-sweep specification."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+from citam_b200 import sweep  # noqa: E402
+
+
+def test_block_starts_spread_over_the_day_and_disjoint_across_ranks():
+    T, block, K = 28_800, 240, 12
+    for world in (1, 2, 8):
+        starts = sorted(s for r in range(world) for s in bench.block_starts(T, block, K, r, world))
+        assert len(starts) == K * world == len(set(starts))
+        assert starts[0] >= 0 and starts[-1] + block <= T
+        gaps = [b - a for a, b in zip(starts[:-1], starts[1:])]
+        assert min(gaps) >= block or world * K * block > T  # blocks of one run do not overlap
+        assert starts[-1] > T * 0.8 and starts[0] < T * 0.2  # the whole day is sampled
+    # warm-up blocks use other offsets than the timed ones
+    assert set(bench.block_starts(T, block, 3, 0, 1, offset=3)).isdisjoint(bench.block_starts(T, block, K, 0, 1))
+
+
+def test_auto_block_and_profile_lookup():
+    assert bench.auto_block(dict(n_agents=1_000_000)) == 240
+    assert bench.auto_block(dict(n_agents=10_000)) == 960
+    assert bench.auto_block(dict(n_agents=200_000, social=0.85)) == 48
+    t = bench.profiled_traffic("accumulate")
+    assert t is None or t > 1e9
+    assert bench.profiled_traffic("no_such_kernel") is None
+    peak, src = bench.peaks()
+    assert 3000 < peak < 9000 and src
+
+
+def test_sweep_specification_covers_the_grid():
+    specs = sweep.make_sweep(1024)
+    assert len(specs) == 1024 and [s.replica for s in specs] == list(range(1024))
+    combos = {(s.n_agents, s.n_shifts, s.contact_distance) for s in specs}
+    assert len(combos) == 64  # 4 occupancies x 4 shift counts x 4 distances
+    assert {s.n_agents for s in specs} == {625, 1250, 1875, 2500}
+    assert len({s.seed for s in specs}) == 16
+    from citam_b200.distributed import plan_replicas
+
+    mine = [plan_replicas(1024, 8, r) for r in range(8)]
+    assert sorted(i for m in mine for i in m) == list(range(1024)) and all(len(m) == 128 for m in mine)
