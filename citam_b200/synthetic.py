@@ -205,7 +205,10 @@ def _make_batch(fac, a0, a1, n_agents, T, n_shifts, seed, n_stops, entry_window,
     ids = np.arange(a0, a1, dtype=np.int64)
     F = fac.n_floors
     floor = (ids % F).astype(np.int32)
-    shift = ((ids // F) % n_shifts).astype(np.int64)
+    # agents of one shift have consecutive ids, as in the reference, whose scheduler appends the
+    # schedules shift by shift and numbers agents in that order
+    # (office_scheduler.py:146-225, simulation.py:277-289)
+    shift = np.minimum(ids * n_shifts // max(1, n_agents), n_shifts - 1).astype(np.int64)
     shift_len = T // n_shifts
     offices0, offices1 = fac.rooms_of_kind(KIND_OFFICE, True), fac.rooms_of_kind(KIND_OFFICE, False)
 
