@@ -96,7 +96,11 @@ EXPORTS = [
     "citam_pair_count", "citam_export_pairs", "citam_export_agent_durations", "citam_coord_count",
     "citam_export_coords", "citam_export_contact_log", "citam_clear_contact_log", "citam_statistics", "citam_get_counters",
     "citam_get_timings", "citam_agent_durations_device", "citam_merge_pairs", "citam_merge_coords",
+    "citam_hist_device", "citam_export_pairs_device", "citam_export_coords_device", "citam_partition_pairs_device",
+    "citam_clear_pairs", "citam_merge_pairs_device", "citam_statistics_begin", "citam_stats_arrays_device",
+    "citam_statistics_end",
 ]
+ABI_VERSION = 2
 
 _lib = None
 
@@ -144,11 +148,22 @@ def load() -> C.CDLL:
         "citam_agent_durations_device": (C.c_int, [vp, C.POINTER(vp), pu64]),
         "citam_merge_pairs": (C.c_int, [vp, vp, u64]),
         "citam_merge_coords": (C.c_int, [vp, vp, u64]),
+        "citam_hist_device": (C.c_int, [vp, C.POINTER(vp), pu64]),
+        "citam_export_pairs_device": (C.c_int, [vp, vp, u64, pu64]),
+        "citam_export_coords_device": (C.c_int, [vp, vp, u64, pu64]),
+        "citam_partition_pairs_device": (C.c_int, [vp, vp, u64, i32, pu64]),
+        "citam_clear_pairs": (C.c_int, [vp]),
+        "citam_merge_pairs_device": (C.c_int, [vp, vp, u64]),
+        "citam_statistics_begin": (C.c_int, [vp]),
+        "citam_stats_arrays_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), pu64]),
+        "citam_statistics_end": (C.c_int, [vp, C.POINTER(Stats)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.citam_abi_version() != ABI_VERSION:
+        raise CitamDeviceError(ERR_STATE, "%s is ABI %d, this package expects %d: rebuild it" % (LIB_PATH, lib.citam_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

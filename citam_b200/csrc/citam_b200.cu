@@ -7,25 +7,29 @@
 //   CloseContactsCalculator.run               citam/engine/calculators/close_contacts_calculator.py:64-231
 //   ContactEvents.add_contact / statistics    citam/engine/calculators/contacts.py:92-294
 //
-// Pipeline per chunk of S <= 256 time steps (one launch per stage covers all steps of the chunk;
+// Pipeline per chunk of S <= 1024 time steps (one launch per stage covers all steps of the chunk;
 // every accumulator is commutative, so steps, chunks and time blocks are independent):
-//   k_expand_bin      itinerary segments -> per-step 16-byte records {x, y, state word, rank}; one
-//                     atomic per located agent returns its rank in its uniform-grid cell
+//   k_expand_bin      itinerary segments -> per-step 16-byte records {xy, until, state word, rank};
+//                     one atomic per located agent returns its rank in its uniform-grid cell
 //   k_scan(+_add)     per-step exclusive scan of the cell histogram (rows x pieces CTAs)
 //   k_scatter         counting-sort scatter into cell order (16-byte records)
 //   k_select_changed  per step, the agents whose state may differ from the step before, in cell order
-//   k_pairs           first step of the chunk: every located agent against its half neighbourhood
-//                     (own cell tail, right cell, 3 cells above), candidate window in shared memory
-//   k_pairs_changed   other steps: only changed agents, 3x3 neighbourhood, tests flattened over a
-//                     256-agent batch; a contact of two unchanged agents is inside a run that an
-//                     earlier step added in one piece (stationary-run aggregation)
+//   k_pairs           first step of a citam_run RANGE only: every located agent against its half
+//                     neighbourhood (own cell tail, right cell, 3 cells above), window in shared memory
+//   k_pairs_changed   every other step: only changed agents, 3x3 neighbourhood, tests flattened over
+//                     a 256-agent batch; a contact of two unchanged agents is inside a run that an
+//                     earlier step added in one piece (stationary-run aggregation: ONE table update
+//                     per contact run, however many chunks the run crosses)
 //   k_accumulate      (side stream, overlaps the next chunk) one contact-run record per thread:
-//                     16-byte pair-table slot probe + one CAS, one 64-bit reduction into the dense
+//                     16-byte pair-table slot probe + one reduction, one 64-bit reduction into the dense
 //                     per-coordinate histogram, two reductions into the L2-resident per-agent counters
+// Finalize (K5): compaction of the tables + device radix sort (radix_sort.cuh) into the reference's
+// output order; partition by key hash for the multi-GPU all-to-all; merge of received records.
 // The distance predicate is the reference's float64 sqrt(dx^2+dy^2) < D as an exact integer
 // threshold (find_s_max).  All of this is HBM/L2-bound integer work; there is no GEMM in the path.
 
 #include "../../include/citam_b200.h"
+#include "radix_sort.cuh"
 
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -103,7 +107,7 @@ struct __align__(16) CoordEntry {
 // One detected contact run, appended by k_pairs and applied by k_accumulate.
 struct __align__(16) ContactRec {
   uint32_t a1, a2;   // a1 < a2
-  uint32_t t_run;    // step (24 bits) | (run - 1) << 24
+  uint32_t t_run;    // step - chunk_begin (12 bits) | (run - 1) << 12 (run <= 2^20 steps)
   uint32_t bucket;   // dense-histogram bucket (30 bits) | bit 31: in contact at t-1 | bit 30: evaluate that at accumulation
 };
 
@@ -130,24 +134,28 @@ struct Params {
   int32_t cell;
   int32_t total_cells;
   int32_t cells_stride;  // uint32 per step row of the histogram (>= total_cells+1, multiple of 4)
+  uint32_t cell_magic;  // floor(2^32 / cell) + 1: x / cell == __umulhi(x, cell_magic) for x < 2^16 (cell > 1)
+  uint32_t d_lim;       // floor(sqrt(s_max)): |dx|, |dy| beyond it cannot be in contact
   double D;
-  long long s_max;  // largest integer s with sqrt_rn((double)s) < D  (-1: none)
+  unsigned long long s_lim;  // s_max + 1, where s_max is the largest integer s with sqrt_rn((double)s) < D (0: none)
   const FloorDev* floors;
   const int4* segs;  // {t0 | floor<<24, x0, y0, dx&0xffff | dy<<16}
   const long long* seg_off;
   const int2* window;  // per agent {first step in the facility, first step of a final stay outside every space}
                        // (INT_MAX when there is none); NULL = not available
-  int4* rec;        // [(S+1)][N] {x, y, state word, rank in cell}; row 0 = halo step t_begin-1
+  int4* rec;        // [(S+1)][N] row 0 = halo step t_begin-1.  Located agent: {xy, until, state word, rank in
+                    // cell}; in the facility but in no space: {x, y, state word, 0}; else {0, 0, state word, 0}
   uint32_t* cells;  // [S][cells_stride]
-  int4* sorted;     // [S][N] {x, y, agent, state word} in cell order
+  int4* sorted;     // [S][N] {xy, agent, state word, until} in cell order
   PairEntry* pairs;
   unsigned long long pair_mask;
   CoordEntry* coords;     // hashed histogram (lattices too large for the dense one)
   unsigned long long coord_mask;
   unsigned long long* hist;  // dense histogram, NULL = use the hash
   int32_t range_begin;       // first step of the current citam_run range
+  int32_t range_end;         // its end: contact runs are clipped here
   int32_t chunk_begin;       // first step of the chunk being processed
-  citam_contact* log;
+  uint4* log;                // {step, a1, a2, 0}
   unsigned long long log_cap;
   ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
   unsigned long long cbuf_sub_cap;
@@ -165,26 +173,28 @@ struct Params {
 #define OVF_FIELD 16ULL
 
 // state word: bits 0-14 space index (0x7fff = none); bit 15 "changed": the agent is NOT known to
-// be exactly where it was one step earlier (it moves, or this is the first step of its segment);
-// bits 16-23: for a still agent "stay" = for how many following steps of this chunk the state is
-// guaranteed identical (same zero-velocity segment); for a moving agent (bit 30) the step it
-// just made, (dx+8) | (dy+8) << 4, or 0 when that is not known here (first step of a segment, a
-// stride beyond +-7); bits 24-29 floor; bit 31 = not in the facility.  changed/stay come from the
-// segment store alone, so they agree with each other: changed(t+k) == 0 for k = 1..stay(t) and
-// changed(t+stay+1) == 1 (or the chunk ends).
-constexpr int kMaxChunk = 256;  // stay must fit 8 bits
+// be exactly where (and what) it was one step earlier (it moves, or this is the first step of its
+// segment); bits 24-29 floor; bit 30 moving; bit 31 = not in the facility.
+// xy: lattice-relative position of a LOCATED agent, (x - minx) | (y - miny) << 16 (an agent has a
+// space only inside its floor's location table, whose sides are <= 65536).
+// until: the first step at which the agent's state may differ from the current one -- the start of
+// its next segment for an agent standing in a zero-velocity segment, t + 1 otherwise.  changed and
+// until come from the segment store alone, so they agree with each other: for a still agent
+// changed(t') == 0 for t < t' < until(t), whatever chunk t' falls into.
+constexpr int kMaxChunk = 1024;     // steps per launch group (12 bits in ContactRec.t_run: <= 4096)
+constexpr int kMaxRunLog2 = 20;     // a contact run is clipped to 2^20 steps: longer citam_run ranges are split
 constexpr int kMaxFloors = 63;
-__device__ __forceinline__ int32_t pack_fl(int floor, int loc, int changed = 1, int stay = 0, int moving = 0) {
+__device__ __forceinline__ int32_t pack_fl(int floor, int loc, int changed = 1, int moving = 0) {
   if (floor < 0) return (int32_t)0x8000ffffu;
-  return (int32_t)(((uint32_t)(moving & 1) << 30) | ((uint32_t)(floor & 0x3f) << 24) | ((uint32_t)(stay & 0xff) << 16) |
+  return (int32_t)(((uint32_t)(moving & 1) << 30) | ((uint32_t)(floor & 0x3f) << 24) |
                    ((uint32_t)(changed & 1) << 15) | ((uint32_t)loc & 0x7fffu));
 }
 __device__ __forceinline__ int fl_floor(int32_t fl) { return fl < 0 ? -1 : (fl >> 24) & 0x3f; }
 __device__ __forceinline__ int fl_loc(int32_t fl) { int v = fl & 0x7fff; return v == 0x7fff ? -1 : v; }
 __device__ __forceinline__ bool fl_changed(int32_t fl) { return (fl >> 15) & 1; }
-__device__ __forceinline__ bool fl_moving(int32_t fl) { return (fl >> 30) & 1; }
-__device__ __forceinline__ int fl_stay(int32_t fl) { return fl_moving(fl) ? 0 : (fl >> 16) & 0xff; }
-__device__ __forceinline__ int fl_step_code(int32_t fl) { return fl_moving(fl) ? (fl >> 16) & 0xff : 0; }
+__device__ __forceinline__ bool fl_located(int32_t fl) { return fl >= 0 && (fl & 0x7fff) != 0x7fff; }
+__device__ __forceinline__ int xy_x(int32_t xy) { return xy & 0xffff; }
+__device__ __forceinline__ int xy_y(int32_t xy) { return (int)((uint32_t)xy >> 16); }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33;
@@ -202,9 +212,12 @@ __device__ __forceinline__ int lut_lookup(const FloorDev& fd, int x, int y) {
   return (int)__ldg(fd.lut + (size_t)fy * fd.W + fx);
 }
 
-__device__ __forceinline__ int cell_of(const FloorDev& fd, int cell, int x, int y) {
-  int cx = (x - fd.minx) / cell, cy = (y - fd.miny) / cell;
-  return fd.cell_base + cy * fd.ncx + cx;
+// v / cell for a lattice-relative coordinate v < 2^16 (exact: cell_magic = floor(2^32/cell) + 1)
+__device__ __forceinline__ int div_cell(const Params& p, int v) {
+  return p.cell == 1 ? v : (int)__umulhi((uint32_t)v, p.cell_magic);
+}
+__device__ __forceinline__ int cell_of_xy(const Params& p, const FloorDev& fd, int32_t xy) {
+  return fd.cell_base + div_cell(p, xy_y(xy)) * fd.ncx + div_cell(p, xy_x(xy));
 }
 
 // Per agent, the steps at which it can matter to the loop: before `x` it is not in the facility;
@@ -222,6 +235,25 @@ __global__ void k_agent_windows(Params p, int2* out) {
     if (last.w == 0 && (f >= p.F || lut_lookup(p.floors[f], last.y, last.z) < 0)) w.y = last.x & 0xffffff;
   }
   out[a] = w;
+}
+
+// Checks the limits the header documents on a freshly loaded segment store (one thread per agent):
+// seg_off non-decreasing inside [0, n_segs]; per agent t0 strictly increasing in [0, 2^24 - 2];
+// floor in 0..62; the last segment holds still (the sticky tail).  Any violation sets *bad.
+__global__ void k_validate_segments(const long long* seg_off, const citam_segment* raw, long long n_segs, int N, int* bad) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= N) return;
+  long long sb = seg_off[a], se = seg_off[a + 1];
+  if (sb < 0 || se < sb || se > n_segs) { atomicOr(bad, 1); return; }
+  int prev = -1;
+  for (long long i = sb; i < se; ++i) {
+    citam_segment g = raw[i];
+    if (g.t0 <= prev || g.t0 > 0xFFFFFD) { atomicOr(bad, 2); return; }
+    if (g.floor < 0 || g.floor >= kMaxFloors) { atomicOr(bad, 4); return; }
+    if (g.x0 <= -(1 << 26) || g.x0 >= (1 << 26) || g.y0 <= -(1 << 26) || g.y0 >= (1 << 26)) { atomicOr(bad, 16); return; }
+    prev = g.t0;
+    if (i == se - 1 && (g.dx != 0 || g.dy != 0)) { atomicOr(bad, 8); return; }
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -279,62 +311,62 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
       loc = (f < p.F) ? lut_lookup(p.floors[f], x, y) : -1;
       lastx = x; lasty = y; lastf = f;
     }
-    // stationary inside one segment: same state as the step before / for `stay` more steps
+    // stationary inside one segment: same state as the step before, and until the next segment starts
     const bool still = s.w == 0;
-    int changed = !(still && dt >= 1);
-    int stay = still ? min(min(next_t0 - 1 - t, rows - 1 - row), kMaxChunk - 1) : 0;
-    if (!still) {  // the step just made, when it is this segment's stride
-      int vx = (int)(int16_t)(s.w & 0xffff), vy = (int)(int16_t)((uint32_t)s.w >> 16);
-      stay = (dt >= 1 && vx >= -7 && vx <= 7 && vy >= -7 && vy <= 7) ? ((vx + 8) | ((vy + 8) << 4)) : 0;
+    const int changed = !(still && dt >= 1);
+    if (loc < 0) {  // in the facility, in no space: never binned, never in contact
+      p.rec[o] = make_int4(x, y, pack_fl(f, -1, changed, still ? 0 : 1), 0);
+      continue;
     }
-    uint32_t rk = 0;
-    if (do_bin && row >= 1 && loc >= 0) {
-      int key = cell_of(p.floors[f], p.cell, x, y);
-      rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
-    }
-    p.rec[o] = make_int4(x, y, pack_fl(f, loc, changed, stay, still ? 0 : 1), (int)rk);
-  }
-}
-
-// K1b: histogram from caller-supplied state rows (the Calculator.run entry).
-__global__ void k_bin_states(Params p, int rows) {
-  int a = blockIdx.x * blockDim.x + threadIdx.x;
-  int row = blockIdx.y + 1;
-  if (a >= p.N || row >= rows) return;
-  size_t o = (size_t)row * p.N + a;
-  int4 r = p.rec[o];
-  int f = fl_floor(r.z), loc = fl_loc(r.z);
-  if (f < 0 || loc < 0) return;
-  bool ok = f < p.F;
-  if (ok) {
     const FloorDev& fd = p.floors[f];
-    int fx = r.x - fd.minx, fy = r.y - fd.miny;
-    ok = fd.lut != nullptr && (unsigned)fx < (unsigned)fd.W && (unsigned)fy < (unsigned)fd.H;
+    const int32_t xy = (x - fd.minx) | ((y - fd.miny) << 16);
+    uint32_t rk = 0;
+    if (do_bin && row >= 1)
+      rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + cell_of_xy(p, fd, xy)], 1u);
+    p.rec[o] = make_int4(xy, still ? next_t0 : t + 1, pack_fl(f, loc, changed, still ? 0 : 1), (int)rk);
   }
-  if (!ok) {  // caller says "located" but the point is outside the floor's grid
-    atomicOr(&p.ctr->overflow, OVF_GRID);
-    p.rec[o].z = pack_fl(f, -1);
-    return;
-  }
-  int key = cell_of(p.floors[f], p.cell, r.x, r.y);
-  p.rec[o].w = (int)atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + key], 1u);
 }
 
-__global__ void k_states_to_rec(const citam_agent_state* st, int N, int4* rec) {
+// K1b: the Calculator.run entry: caller-supplied states -> record row (+ histogram).
+__global__ void k_states_to_rec(Params p, const citam_agent_state* st, int4* rec, int step, int do_bin) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= N) return;
+  if (a >= p.N) return;
   citam_agent_state s = st[a];
   int f = s.floor < 0 ? -1 : s.floor;
   int l = (f < 0 || s.loc < 0) ? -1 : s.loc;
-  rec[a] = make_int4(s.x, s.y, pack_fl(f, l), 0);
+  if (f < 0) { rec[a] = make_int4(0, 0, pack_fl(-1, -1), 0); return; }
+  if (l >= 0) {
+    bool ok = f < p.F;
+    if (ok) {
+      const FloorDev& fd = p.floors[f];
+      int fx = s.x - fd.minx, fy = s.y - fd.miny;
+      ok = fd.lut != nullptr && (unsigned)fx < (unsigned)fd.W && (unsigned)fy < (unsigned)fd.H && l < fd.n_spaces;
+    }
+    if (!ok) {  // caller says "located" but the point is outside the floor's grid
+      atomicOr(&p.ctr->overflow, OVF_GRID);
+      l = -1;
+    }
+  }
+  if (l < 0) { rec[a] = make_int4(s.x, s.y, pack_fl(f & 0x3f, -1), 0); return; }
+  const FloorDev& fd = p.floors[f];
+  const int32_t xy = (s.x - fd.minx) | ((s.y - fd.miny) << 16);
+  uint32_t rk = 0;
+  if (do_bin) rk = atomicAdd(&p.cells[cell_of_xy(p, fd, xy)], 1u);
+  rec[a] = make_int4(xy, step + 1, pack_fl(f, l), (int)rk);
 }
 
-__global__ void k_rec_to_states(const int4* rec, long long N, citam_agent_state* st) {
+__global__ void k_rec_to_states(Params p, const int4* rec, long long N, citam_agent_state* st) {
   long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= N) return;
   int4 r = rec[a];
   citam_agent_state s;
-  s.x = r.x; s.y = r.y; s.floor = (int16_t)fl_floor(r.z); s.loc = (int16_t)fl_loc(r.z);
+  s.floor = (int16_t)fl_floor(r.z); s.loc = (int16_t)fl_loc(r.z);
+  if (fl_located(r.z)) {
+    const FloorDev& fd = p.floors[s.floor];
+    s.x = xy_x(r.x) + fd.minx; s.y = xy_y(r.x) + fd.miny;
+  } else {
+    s.x = r.x; s.y = r.y;
+  }
   st[a] = s;
 }
 
@@ -431,26 +463,25 @@ __global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */, int
     if (t < win.x || t >= win.y) return;
   }
   int4 r = p.rec[(size_t)(row + 1) * p.N + a];
-  int f = fl_floor(r.z), loc = fl_loc(r.z);
-  if (f < 0 || loc < 0) return;
-  int key = cell_of(p.floors[f], p.cell, r.x, r.y);
+  if (!fl_located(r.z)) return;
+  int key = cell_of_xy(p, p.floors[fl_floor(r.z)], r.x);
   uint32_t dest = p.cells[(size_t)row * p.cells_stride + key] + (uint32_t)r.w;
-  p.sorted[(size_t)row * p.N + dest] = make_int4(r.x, r.y, a, r.z);
+  p.sorted[(size_t)row * p.N + dest] = make_int4(r.x, a, r.z, r.y);
 }
 
 // K3b: per step, the sorted positions of the agents whose state may have changed, compacted in
 // CELL ORDER (each warp appends its 32 consecutive sorted positions' hits in one piece), so that
 // neighbouring threads of k_pairs_changed work on neighbouring agents: their candidate ranges
 // overlap (L1 hits) and their histogram buckets share sectors.
-__global__ void __launch_bounds__(256) k_select_changed(Params p, int rows /* S */) {
-  const int row = blockIdx.y + 1;  // the first step of a chunk is handled by k_pairs in full
+__global__ void __launch_bounds__(256) k_select_changed(Params p, int row0, int rows /* S */) {
+  const int row = blockIdx.y + row0;  // a range's first step is handled by k_pairs in full
   if (row >= rows) return;
   const int total = (int)p.cells[(size_t)row * p.cells_stride + p.total_cells];
   const int lane = threadIdx.x & 31;
   for (int q0 = blockIdx.x * blockDim.x; q0 < total; q0 += gridDim.x * blockDim.x) {
     const int q = q0 + threadIdx.x;
     bool sel = false;
-    if (q < total) sel = fl_changed(p.sorted[(size_t)row * p.N + q].w);
+    if (q < total) sel = fl_changed(p.sorted[(size_t)row * p.N + q].z);
     unsigned m = __ballot_sync(0xffffffffu, sel);
     if (m == 0) continue;
     uint32_t base = 0;
@@ -482,9 +513,14 @@ __device__ __forceinline__ bool loc_rule_ordered(const FloorDev& fd, int ida, in
 // integers, so s = dx^2+dy^2 is exact, and s -> sqrt_rn((double)s) is monotone: the predicate
 // holds exactly for s <= s_max, where the host found s_max with the same IEEE operations
 // (find_s_max) and citam_create checked it on the device against __dsqrt_rn (k_check_s_max).
+// |dx|, |dy| < 2^16 (lattice-relative), so each square fits 32 bits.
 __device__ __forceinline__ bool within(int dx, int dy, const Params& p) {
-  long long s = (long long)dx * dx + (long long)dy * dy;
-  return s <= p.s_max;
+  const uint32_t ax = (uint32_t)abs(dx), ay = (uint32_t)abs(dy);
+  if (max(ax, ay) > p.d_lim) return false;
+  return (unsigned long long)(ax * ax) + (unsigned long long)(ay * ay) < p.s_lim;
+}
+__device__ __forceinline__ bool within_xy(int32_t xy1, int32_t xy2, const Params& p) {
+  return within(xy_x(xy2) - xy_x(xy1), xy_y(xy2) - xy_y(xy1), p);
 }
 
 // Linear probing is bounded: a table that needs more probes than this is reported as full
@@ -525,11 +561,40 @@ __device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigne
   return ~0ULL;
 }
 
+// Apply add_dur contact-steps and add_nev events to the slot; `first` (a step, or NO_STEP) lowers
+// the pair's first-contact step.  The first contact of a pair is always an event start, so callers
+// pass a step only for event starts and for the first step of a run range.
+// `old` is the accumulator word the probe saw.  While it is far from the field limits (less than
+// half way: no set of concurrent updates of one pair can cover the other half, a pair gets at most
+// one record per step) and the first-contact field cannot move, the update is a plain addition on
+// the packed word -- one reduction, no round trip, no retry.  Otherwise a compare-and-swap loop
+// that checks the limits on the live value.
+__device__ __forceinline__ void pair_apply_acc(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
+                                               unsigned long long add_dur, unsigned long long add_nev) {
+  unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
+  if (finv <= ACC_FIRST_INV(old) && ACC_DUR(old) + add_dur <= 0x7fffffULL && ACC_NEV(old) + add_nev <= 0x7fffULL) {
+    atomicAdd(&p.pairs[h].acc, add_dur | (add_nev << 24));
+    return;
+  }
+  for (;;) {
+    unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
+    if (d > 0xffffffULL || n > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
+    unsigned long long f = max((unsigned long long)ACC_FIRST_INV(old), finv);
+    unsigned long long seen = atomicCAS(&p.pairs[h].acc, old, d | (n << 24) | (f << 40));
+    if (seen == old) return;
+    old = seen;
+  }
+}
+
+// The same plus the contact-steps on both agents' counters (close_contacts_calculator.py:221-224):
+// the counter array is N x 8 bytes, L2-resident, so these two reductions cost no DRAM access.
 __device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
-                                           unsigned long long add_dur, unsigned long long add_nev, uint32_t a1, uint32_t a2);
-// add_dur contact-steps and add_nev events; `first` (a step, or NO_STEP) lowers the pair's
-// first-contact step.  The first contact of a pair is always an event start, so callers pass a
-// step only for event starts and for the first step of a run range.
+                                           unsigned long long add_dur, unsigned long long add_nev, uint32_t a1, uint32_t a2) {
+  atomicAdd(&p.agent_dur[a1], add_dur);
+  atomicAdd(&p.agent_dur[a2], add_dur);
+  pair_apply_acc(p, h, old, first, add_dur, add_nev);
+}
+
 __device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32_t a2, uint32_t first,
                                             unsigned long long add_dur, unsigned long long add_nev) {
   unsigned long long key = ((unsigned long long)a1 << 32) | a2;
@@ -539,13 +604,14 @@ __device__ __forceinline__ void pair_upsert(const Params& p, uint32_t a1, uint32
   pair_apply(p, h, old, first, add_dur, add_nev, a1, a2);
 }
 
-__device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx, int sy, unsigned long long add) {
+// ix, iy: lattice-relative contact position x 2 (the sum of the two agents' relative coordinates)
+__device__ __forceinline__ void coord_upsert_rel(const Params& p, int floor, int ix, int iy, unsigned long long add) {
+  const FloorDev& fd = p.floors[floor];
   if (p.hist != nullptr) {  // dense: one reduction, no probe
-    const FloorDev& fd = p.floors[floor];
-    long long ix = (long long)sx - 2LL * fd.minx, iy = (long long)sy - 2LL * fd.miny;
-    atomicAdd(p.hist + fd.hist_base + iy * fd.hist_w + ix, add);
+    atomicAdd(p.hist + fd.hist_base + (long long)iy * fd.hist_w + ix, add);
     return;
   }
+  const int sx = ix + 2 * fd.minx, sy = iy + 2 * fd.miny;
   unsigned long long key = (1ULL << 63) | ((unsigned long long)(floor & 0x7f) << 56) |
                            ((unsigned long long)((uint32_t)(sx + (1 << 27)) & 0xfffffffu) << 28) |
                            (unsigned long long)((uint32_t)(sy + (1 << 27)) & 0xfffffffu);
@@ -569,57 +635,30 @@ __device__ __forceinline__ void coord_upsert(const Params& p, int floor, int sx,
 // (contacts.py:131-133: an event continues iff last.start_step + last.duration == step).
 // One 16-byte record per agent: two sector reads.
 __device__ __forceinline__ bool contact_eval(const Params& p, const int4& r1, const int4& r2) {
-  int fl1 = fl_floor(r1.z), fl2 = fl_floor(r2.z);
-  int l1 = fl_loc(r1.z), l2 = fl_loc(r2.z);
-  if (fl1 < 0 || fl1 != fl2 || l1 < 0 || l2 < 0) return false;
-  long long dx = (long long)r2.x - r1.x, dy = (long long)r2.y - r1.y;
-  long long lim = (long long)p.D + 1;
-  if (dx > lim || dx < -lim || dy > lim || dy < -lim) return false;
-  if (!within((int)dx, (int)dy, p)) return false;
-  return loc_rule(p.floors[fl1], l1, l2);
+  if (!fl_located(r1.z) || !fl_located(r2.z)) return false;
+  const int fl1 = fl_floor(r1.z);
+  if (fl1 != fl_floor(r2.z)) return false;
+  if (!within_xy(r1.x, r2.x, p)) return false;
+  return loc_rule(p.floors[fl1], fl_loc(r1.z), fl_loc(r2.z));
 }
 __device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
   return contact_eval(p, p.rec[prow_off + a1], p.rec[prow_off + a2]);
 }
 
-// pair_upsert split in two so that a caller can put independent loads between probe and update.
-// Also adds the contact-steps to both agents' counters (close_contacts_calculator.py:221-224): the
-// counter array is N x 8 bytes, L2-resident, so these two reductions cost no DRAM access.
-__device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
-                                           unsigned long long add_dur, unsigned long long add_nev, uint32_t a1, uint32_t a2) {
-  atomicAdd(&p.agent_dur[a1], add_dur);
-  atomicAdd(&p.agent_dur[a2], add_dur);
-  unsigned long long finv = first == NO_STEP ? 0ULL : (unsigned long long)(0xFFFFFFu - (first & 0xFFFFFFu));
-  if (finv <= ACC_FIRST_INV(old)) {
-    // the first-contact field cannot move (it only grows, and ours is not larger): the update is a
-    // plain addition on the packed word -- one reduction, no round trip, no retry
-    if (ACC_DUR(old) + add_dur > 0xffffffULL || ACC_NEV(old) + add_nev > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
-    atomicAdd(&p.pairs[h].acc, add_dur | (add_nev << 24));
-    return;
-  }
-  for (;;) {
-    unsigned long long d = ACC_DUR(old) + add_dur, n = ACC_NEV(old) + add_nev;
-    if (d > 0xffffffULL || n > 0xffffULL) { atomicOr(&p.ctr->overflow, OVF_FIELD); return; }
-    unsigned long long f = max((unsigned long long)ACC_FIRST_INV(old), finv);
-    unsigned long long seen = atomicCAS(&p.pairs[h].acc, old, d | (n << 24) | (f << 40));
-    if (seen == old) return;
-    old = seen;
-  }
-}
-
 // A contact found at step t that lasts `run` steps (both agents provably stay put for run-1
-// more steps of this chunk): one table update for the whole run.  `was`: the pair was already in
+// more steps of the range): one table update for the whole run.  `was`: the pair was already in
 // contact at t-1 (the event continues, contacts.py:131-133); `late`: not decided yet -- evaluate the
 // predicate on the previous record row when the record is applied.
+// me / ot are sorted records {xy, agent, state word, until}.
 __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const int4& me, const int4& ot, uint32_t run,
                                            bool was, int sub, bool late = false) {
-  uint32_t a1 = (uint32_t)min(me.z, ot.z), a2 = (uint32_t)max(me.z, ot.z);
-  const int floor = fl_floor(me.w);
+  uint32_t a1 = (uint32_t)min(me.y, ot.y), a2 = (uint32_t)max(me.y, ot.y);
+  const int floor = fl_floor(me.z);
+  const int ix = xy_x(me.x) + xy_x(ot.x), iy = xy_y(me.x) + xy_y(ot.x);
   if (p.cbuf != nullptr) {
     // warp-aggregated append into the chunk's contact buffer; k_accumulate applies it
     const FloorDev& fd = p.floors[floor];
-    uint32_t ix = (uint32_t)((me.x + ot.x) - 2 * fd.minx), iy = (uint32_t)((me.y + ot.y) - 2 * fd.miny);
-    uint32_t bucket = ((uint32_t)fd.hist_base + iy * (uint32_t)fd.hist_w + ix) | (was ? 0x80000000u : 0u);
+    uint32_t bucket = ((uint32_t)fd.hist_base + (uint32_t)iy * (uint32_t)fd.hist_w + (uint32_t)ix) | (was ? 0x80000000u : 0u);
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long base = 0;
     if (g.thread_rank() == 0)
@@ -627,7 +666,7 @@ __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const in
     base = g.shfl(base, 0) + g.thread_rank();
     if (base < p.cbuf_sub_cap) {
       ContactRec r;
-      r.a1 = a1; r.a2 = a2; r.t_run = (t & 0xffffffu) | ((run - 1u) << 24);
+      r.a1 = a1; r.a2 = a2; r.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
       r.bucket = late ? (bucket & 0x3fffffffu) | 0x40000000u : bucket;  // bit 30: evaluate `was` in k_accumulate
       p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + base] = r;
       return;
@@ -637,7 +676,7 @@ __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const in
   if (late) was = contact_prev(p, (size_t)((int)t - p.chunk_begin) * p.N, a1, a2);
   uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
   pair_upsert(p, a1, a2, first, run, was ? 0u : 1u);
-  coord_upsert(p, floor, me.x + ot.x, me.y + ot.y, (unsigned long long)run);
+  coord_upsert_rel(p, floor, ix, iy, (unsigned long long)run);
   if (p.log_cap) {
     // warp-aggregated append: one atomic per converged group of lanes
     cg::coalesced_group g = cg::coalesced_threads();
@@ -645,12 +684,16 @@ __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const in
     if (g.thread_rank() == 0) base = atomicAdd(&p.ctr->log_count, (unsigned long long)g.size());
     base = g.shfl(base, 0) + g.thread_rank();
     if (base < p.log_cap) {
-      citam_contact c; c.step = t; c.a1 = a1; c.a2 = a2;
-      p.log[base] = c;
+      p.log[base] = make_uint4(t, a1, a2, 0u);
     } else {
       atomicOr(&p.ctr->overflow, OVF_LOG);
     }
   }
+}
+
+// steps a contact found at t lasts: until either agent's state may change, or the range ends
+__device__ __forceinline__ uint32_t run_length(const Params& p, int until_a, int until_b, uint32_t t) {
+  return (uint32_t)(min(min(until_a, until_b), p.range_end) - (int)t);
 }
 
 // One thread per located agent of one step ("me", in cell order) walks its half neighbourhood:
@@ -659,35 +702,38 @@ __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const in
 // block stages in shared memory with coalesced 16-byte loads, so the per-candidate loop runs at
 // shared-memory latency (windows beyond kWindow records are read from global memory instead).
 //
-// Stationary-run aggregation: a pair whose two agents are both provably where they were one step
-// earlier (changed == 0) was handled at the step its run started -- by the owner step's thread,
-// which added the whole run (1 + min(stay_me, stay_ot) steps, clipped to the chunk) in one
-// update -- so later steps of the run skip it without a distance evaluation.  The first step of
-// a chunk owns everything it finds.  With the contact log on, every contact-step is evaluated
-// and logged on its own (aggregate == 0).
+// Run for the FIRST step of a citam_run range, which owns every contact it finds and adds the
+// whole run (until either agent's state may change, clipped to the range) in one update; later
+// steps only look at agents whose state may have changed (k_pairs_changed).  With the contact log
+// on, every step is evaluated here in full and logged contact-step by contact-step (aggregate == 0).
 constexpr int kPairThreads = 256;
 constexpr int kWindow = 2560;  // records (40 KB)
 
 __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, int rows /* S */, int aggregate) {
   __shared__ int4 win[kWindow];
   __shared__ int s_w1;
+  __shared__ int s_void;
   const int row = blockIdx.y;
   const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
   const int total = (int)cs[p.total_cells];
   const int w0 = blockIdx.x * kPairThreads;
   if (w0 >= total) return;  // whole block
-  if (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) return;  // results are void already
   const int q0 = w0 + threadIdx.x;
   const int4* srt = p.sorted + (size_t)row * p.N;
-  if (threadIdx.x == 0) s_w1 = w0;
+  if (threadIdx.x == 0) {
+    s_w1 = w0;
+    // results are void already when a table has overflowed: one read per block, the same answer for all its threads
+    s_void = (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) != 0;
+  }
   __syncthreads();
+  if (s_void) return;
   int4 me = make_int4(0, 0, 0, 0);
   int qa = 0, qa_end = 0, qb = 0, qb_end = 0, f = 0, loc = -1;
   if (q0 < total) {
     me = srt[q0];
-    f = fl_floor(me.w); loc = fl_loc(me.w);
+    f = fl_floor(me.z); loc = fl_loc(me.z);
     const FloorDev& fd = p.floors[f];
-    int cx = (me.x - fd.minx) / p.cell, cy = (me.y - fd.miny) / p.cell;
+    int cx = div_cell(p, xy_x(me.x)), cy = div_cell(p, xy_y(me.x));
     int rowbase = fd.cell_base + cy * fd.ncx;
     qa = q0 + 1;
     qa_end = (int)cs[rowbase + min(cx + 1, fd.ncx - 1) + 1];
@@ -711,23 +757,20 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
   if (q0 < total) {
     const FloorDev& fd = p.floors[f];
     const uint32_t t = (uint32_t)(t_begin + row);
-    const bool me_still = aggregate && row > 0 && !fl_changed(me.w);
-    const int me_stay = aggregate ? fl_stay(me.w) : 0;
     const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
 #pragma unroll 1
     for (int rg = 0; rg < 2; ++rg) {
       const int qs = rg ? qb : qa, qe = rg ? qb_end : qa_end;
       for (int q = qs; q < qe; ++q) {
         int4 ot = staged ? win[q - w0] : srt[q];
-        if (me_still && !fl_changed(ot.w)) continue;  // inside a run owned by an earlier step
         ++tests;
-        if (within(ot.x - me.x, ot.y - me.y, p) && loc_rule_ordered(fd, me.z, loc, ot.z, fl_loc(ot.w))) {
-          uint32_t run = 1u + (uint32_t)min(me_stay, aggregate ? fl_stay(ot.w) : 0);
+        if (within_xy(me.x, ot.x, p) && loc_rule_ordered(fd, me.y, loc, ot.y, fl_loc(ot.z))) {
+          uint32_t run = aggregate ? run_length(p, me.w, ot.w, t) : 1u;
           hits += run;
           ++runs;
           // both agents exactly where (and what) they were a step ago: in contact then too;
           // otherwise the predicate on the previous record row is evaluated at accumulation
-          const bool known = !fl_changed(me.w) && !fl_changed(ot.w);
+          const bool known = !fl_changed(me.z) && !fl_changed(ot.z);
           on_contact(p, t, me, ot, run, known, sub, !known);
         }
       }
@@ -745,7 +788,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
   }
 }
 
-// Steps after the first of a chunk: only agents whose state may have changed can start, end or
+// Every step but a range's first: only agents whose state may have changed can start, end or
 // move a contact (everything else is inside a run that an earlier step already added).  A block
 // takes a batch of 256 changed agents (in cell order, from the per-step list of k_select_changed);
 // every agent's 3x3 neighbourhood is three contiguous ranges of the sorted array.  The tests of the
@@ -761,19 +804,22 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
 constexpr int kHitSlots = 6;
 constexpr int kPC = 256;
 
-__global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, int rows /* S */) {
+__global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, int row0, int rows /* S */) {
   __shared__ ContactRec hitbuf[kPC * kHitSlots];
   __shared__ int4 s_me[kPC];
   __shared__ int s_qs[3][kPC];
   __shared__ int s_l0[kPC], s_l01[kPC];
-  __shared__ uint32_t s_hb[kPC];
   __shared__ int s_off[kPC + 1];
   __shared__ int s_warp[kPC / 32];
-  const int row = blockIdx.y + 1;
+  __shared__ int s_void;
+  const int row = blockIdx.y + row0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = p.chg_count[row * 32];
   if (blockIdx.x * kPC >= n) return;
-  if (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) return;
+  if (threadIdx.x == 0)
+    s_void = (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) != 0;
+  __syncthreads();
+  if (s_void) return;
   const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
   const int4* srt = p.sorted + (size_t)row * p.N;
   const uint32_t t = (uint32_t)(t_begin + row);
@@ -787,8 +833,8 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
     int total = 0;
     if (idx < n) {
       const int4 me = srt[p.chg_list[(size_t)row * p.N + idx]];
-      const FloorDev& fd = p.floors[fl_floor(me.w)];
-      const int cx = (me.x - fd.minx) / p.cell, cy = (me.y - fd.miny) / p.cell;
+      const FloorDev& fd = p.floors[fl_floor(me.z)];
+      const int cx = div_cell(p, xy_x(me.x)), cy = div_cell(p, xy_y(me.x));
       const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
       const int rb = fd.cell_base + cy * fd.ncx;
       const bool up = cy + 1 < fd.ncy, dn = cy > 0;
@@ -799,7 +845,6 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
       s_me[threadIdx.x] = me;
       s_qs[0][threadIdx.x] = q0; s_qs[1][threadIdx.x] = q1; s_qs[2][threadIdx.x] = q2;
       s_l0[threadIdx.x] = l0; s_l01[threadIdx.x] = l0 + l1;
-      s_hb[threadIdx.x] = (uint32_t)fd.hist_base - (uint32_t)(2 * fd.miny) * (uint32_t)fd.hist_w - (uint32_t)(2 * fd.minx);
       total = l0 + l1 + l2;
     }
     // block exclusive scan of the candidate counts
@@ -830,21 +875,22 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
       const int q = k < l0 ? s_qs[0][i] + k : (k < l01 ? s_qs[1][i] + (k - l0) : s_qs[2][i] + (k - l01));
       const int4 ot = srt[q];
       const int4 me = s_me[i];
-      const int a = me.z;
-      if (ot.z == a) continue;
-      if (fl_changed(ot.w) && ot.z < a) continue;  // that agent owns the pair
+      const int a = me.y;
+      if (ot.y == a) continue;
+      if (fl_changed(ot.z) && ot.y < a) continue;  // that agent owns the pair
       ++tests;
-      if (!within(ot.x - me.x, ot.y - me.y, p)) continue;
-      const FloorDev& fd = p.floors[fl_floor(me.w)];
-      if (!loc_rule_ordered(fd, a, fl_loc(me.w), ot.z, fl_loc(ot.w))) continue;
-      const uint32_t run = 1u + (uint32_t)min(fl_stay(me.w), fl_stay(ot.w));
+      if (!within_xy(me.x, ot.x, p)) continue;
+      const FloorDev& fd = p.floors[fl_floor(me.z)];
+      if (!loc_rule_ordered(fd, a, fl_loc(me.z), ot.y, fl_loc(ot.z))) continue;
+      const uint32_t run = run_length(p, me.w, ot.w, t);
       hits += run;
       ++runs;
       if (buffered && nh < kHitSlots) {
         ContactRec r;
-        r.a1 = (uint32_t)min(a, ot.z); r.a2 = (uint32_t)max(a, ot.z);
-        r.t_run = (t & 0xffffffu) | ((run - 1u) << 24);
-        r.bucket = ((s_hb[i] + (uint32_t)(me.y + ot.y) * (uint32_t)fd.hist_w + (uint32_t)(me.x + ot.x)) & 0x3fffffffu) | 0x40000000u;
+        r.a1 = (uint32_t)min(a, ot.y); r.a2 = (uint32_t)max(a, ot.y);
+        r.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
+        r.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
+                     (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
         mine[nh++] = r;
       } else {
         on_contact(p, t, me, ot, run, false, sub, true);
@@ -867,8 +913,8 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
             p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + wbase + j] = mine[j];
           } else {  // sub-buffer full: apply inline (k_accumulate clamps the count)
             const ContactRec r = mine[j];
-            const uint32_t rt = r.t_run & 0xffffffu, rrun = (r.t_run >> 24) + 1u;
-            bool was = contact_prev(p, (size_t)((int)rt - p.chunk_begin) * p.N, r.a1, r.a2);
+            const uint32_t rt = (uint32_t)p.chunk_begin + (r.t_run & 0xfffu), rrun = (r.t_run >> 12) + 1u;
+            bool was = contact_prev(p, (size_t)(r.t_run & 0xfffu) * p.N, r.a1, r.a2);
             uint32_t first = (!was || (int32_t)rt == p.range_begin) ? rt : NO_STEP;
             pair_upsert(p, r.a1, r.a2, first, rrun, was ? 0u : 1u);
             atomicAdd(p.hist + (r.bucket & 0x3fffffffu), (unsigned long long)rrun);
@@ -892,7 +938,7 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
 // K4b: apply the chunk's contact buffer to the tables.  One record per thread: every thread's
 // table accesses are independent, so the kernel runs at the memory system's random-access rate
 // instead of at the pace of k_pairs' longest neighbour list.  Per record: one 16-byte slot probe
-// + one 64-bit compare-and-swap on the same sector (pair table) and one 64-bit reduction
+// + one 64-bit reduction on the same sector (pair table) and one 64-bit reduction
 // (coordinate histogram); for run starts that are not known continuations also two 16-byte
 // record reads for the previous-step predicate, issued before the probe so they overlap it.
 // many short-lived blocks rather than a persistent grid: the kernel shares the GPU with the next
@@ -907,12 +953,13 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
   const unsigned long long stride = (unsigned long long)(gridDim.x / kSubBuffers) * blockDim.x;
   for (unsigned long long i = (unsigned long long)part * blockDim.x + threadIdx.x; i < n; i += stride) {
     ContactRec r = buf[i];
-    uint32_t t = r.t_run & 0xffffffu, run = (r.t_run >> 24) + 1u;
+    const uint32_t t_rel = r.t_run & 0xfffu, run = (r.t_run >> 12) + 1u;
+    const uint32_t t = (uint32_t)t_begin + t_rel;
     bool was = r.bucket >> 31;
     int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
     const bool late = (r.bucket >> 30) & 1;
     if (late) {
-      size_t prow = (size_t)((int)t - t_begin) * p.N;  // rec row holding step t-1
+      size_t prow = (size_t)t_rel * p.N;  // rec row holding step t-1
       r1 = p.rec[prow + r.a1];
       r2 = p.rec[prow + r.a2];
     }
@@ -1017,10 +1064,23 @@ __global__ void __launch_bounds__(128) k_build_lut(int minx, int miny, int W, in
 }
 
 // --------------------------------------------------------------------------
-// K5: finalize — compaction of the tables and the integer sums of the statistics.
+// K5: finalize — compaction of the tables, device sort into the reference's output order, and the
+// integer sums of the statistics.
 // --------------------------------------------------------------------------
-__global__ void k_compact_pairs(const PairEntry* tab, unsigned long long cap, citam_pair* out,
-                                unsigned long long out_cap, DevCounters* ctr) {
+__device__ __forceinline__ citam_pair entry_to_pair(unsigned long long key, unsigned long long acc) {
+  citam_pair r;
+  r.a1 = (uint32_t)(key >> 32);
+  r.a2 = (uint32_t)(key & 0xffffffffu);
+  uint32_t finv = ACC_FIRST_INV(acc);
+  r.first_step = finv ? 0xFFFFFFu - finv : NO_STEP;
+  r.n_events = ACC_NEV(acc);
+  r.duration = ACC_DUR(acc);
+  return r;
+}
+
+// the occupied slots of the pair table, packed (any order)
+__global__ void k_compact_entries(const PairEntry* tab, unsigned long long cap, PairEntry* out,
+                                  unsigned long long out_cap, DevCounters* ctr) {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   PairEntry e = tab[i];
@@ -1029,19 +1089,42 @@ __global__ void k_compact_pairs(const PairEntry* tab, unsigned long long cap, ci
   unsigned long long base = 0;
   if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
   base = g.shfl(base, 0) + g.thread_rank();
-  if (base >= out_cap) return;
-  citam_pair r;
-  r.a1 = (uint32_t)(e.key >> 32);
-  r.a2 = (uint32_t)(e.key & 0xffffffffu);
-  uint32_t finv = ACC_FIRST_INV(e.acc);
-  r.first_step = finv ? 0xFFFFFFu - finv : NO_STEP;
-  r.n_events = ACC_NEV(e.acc);
-  r.duration = ACC_DUR(e.acc);
-  out[base] = r;
+  if (base < out_cap) out[base] = e;
 }
 
-__global__ void k_compact_coords(const CoordEntry* tab, unsigned long long cap, citam_coord* out,
-                                 unsigned long long out_cap, DevCounters* ctr) {
+__global__ void k_entries_to_pairs(const PairEntry* in, unsigned long long n, citam_pair* out) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PairEntry e = in[i];
+  out[i] = entry_to_pair(e.key, e.acc);
+}
+
+// Sort keys (radix_sort.cuh; word 0 is the least significant).  A PairEntry as uint4 is
+// {a2, a1, acc low, acc high}: pair_contact.csv order is (first contact step, a1, a2).
+struct PairKey {
+  __device__ __forceinline__ uint32_t operator()(const uint4& r, int word) const {
+    return word == 0 ? r.x : (word == 1 ? r.y : (0xFFFFFFu - (r.w >> 8)) & 0xFFFFFFu);
+  }
+};
+struct LogKey {  // {step, a1, a2, 0}: the reference's visiting order (step, a1, a2)
+  __device__ __forceinline__ uint32_t operator()(const uint4& r, int word) const {
+    return word == 0 ? r.z : (word == 1 ? r.y : r.x);
+  }
+};
+struct CoordKey {  // CoordEntry {key, count}: the key is monotone in (floor, sx, sy)
+  __device__ __forceinline__ uint32_t operator()(const uint4& r, int word) const { return word == 0 ? r.x : r.y; }
+};
+
+__global__ void k_log_to_contacts(const uint4* in, unsigned long long n, citam_contact* out) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4 r = in[i];
+  citam_contact c; c.step = r.x; c.a1 = r.y; c.a2 = r.z;
+  out[i] = c;
+}
+
+__global__ void k_compact_coord_entries(const CoordEntry* tab, unsigned long long cap, CoordEntry* out,
+                                        unsigned long long out_cap, DevCounters* ctr) {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   CoordEntry e = tab[i];
@@ -1050,17 +1133,23 @@ __global__ void k_compact_coords(const CoordEntry* tab, unsigned long long cap, 
   unsigned long long base = 0;
   if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
   base = g.shfl(base, 0) + g.thread_rank();
-  if (base >= out_cap) return;
+  if (base < out_cap) out[base] = e;
+}
+
+__global__ void k_coord_entries_to_records(const CoordEntry* in, unsigned long long n, citam_coord* out) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CoordEntry e = in[i];
   citam_coord r;
   r.floor = (int32_t)((e.key >> 56) & 0x7f);
   r.sx = (int32_t)((e.key >> 28) & 0xfffffffu) - (1 << 27);
   r.sy = (int32_t)(e.key & 0xfffffffu) - (1 << 27);
   r.reserved = 0;
   r.count = e.count;
-  out[base] = r;
+  out[i] = r;
 }
 
-// dense histogram: count / compact the non-zero buckets of one floor
+// dense histogram: count the non-zero buckets
 __global__ void k_hist_count(const unsigned long long* hist, long long n, DevCounters* ctr) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long nz = (i < n && hist[i] != 0ULL) ? 1ULL : 0ULL;
@@ -1068,24 +1157,43 @@ __global__ void k_hist_count(const unsigned long long* hist, long long n, DevCou
   if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&ctr->export_cursor, nz);
 }
 
-__global__ void k_hist_compact(const unsigned long long* hist, long long n, int floor, int hist_w, int minx2, int miny2,
-                               citam_coord* out, unsigned long long out_cap, DevCounters* ctr) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long c = hist[i];
+// Dense histogram -> records in (floor, sx, sy) order without a sort: thread j of a floor looks at
+// bucket (ix, iy) = (j / hist_h, j % hist_h), i.e. the floor is walked column by column; pass 1
+// counts the non-zero buckets per CTA, an exclusive scan over all CTAs of all floors gives each CTA
+// its first output index, pass 2 writes (ballot ranks inside the CTA).
+constexpr int kHistThreads = 256;
+__global__ void __launch_bounds__(kHistThreads) k_hist_ordered(const unsigned long long* hist, long long n, int hist_w,
+                                                               int hist_h, int floor, int minx2, int miny2,
+                                                               uint32_t* block_counts, citam_coord* out,
+                                                               unsigned long long out_cap) {
+  __shared__ uint32_t wsum[kHistThreads / 32];
+  const long long j = (long long)blockIdx.x * kHistThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long c = 0;
+  int ix = 0, iy = 0;
+  if (j < n) {
+    ix = (int)(j / hist_h); iy = (int)(j % hist_h);
+    c = hist[(long long)iy * hist_w + ix];
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, c != 0ULL);
+  if (lane == 0) wsum[w] = __popc(m);
+  __syncthreads();
+  if (out == nullptr) {  // pass 1
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int k = 0; k < kHistThreads / 32; ++k) t += wsum[k];
+      block_counts[blockIdx.x] = t;
+    }
+    return;
+  }
   if (c == 0ULL) return;
-  cg::coalesced_group g = cg::coalesced_threads();
-  unsigned long long base = 0;
-  if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
-  base = g.shfl(base, 0) + g.thread_rank();
-  if (base >= out_cap) return;
+  unsigned long long pos = block_counts[blockIdx.x];  // scanned: first output index of this CTA
+  for (int k = 0; k < w; ++k) pos += wsum[k];
+  pos += __popc(m & ((1u << lane) - 1u));
+  if (pos >= out_cap) return;
   citam_coord r;
-  r.floor = floor;
-  r.sx = (int32_t)(i % hist_w) + minx2;
-  r.sy = (int32_t)(i / hist_w) + miny2;
-  r.reserved = 0;
-  r.count = c;
-  out[base] = r;
+  r.floor = floor; r.sx = ix + minx2; r.sy = iy + miny2; r.reserved = 0; r.count = c;
+  out[pos] = r;
 }
 
 __global__ void k_rehash_pairs(Params p, const PairEntry* old_tab, unsigned long long old_cap) {
@@ -1097,6 +1205,46 @@ __global__ void k_rehash_pairs(Params p, const PairEntry* old_tab, unsigned long
   unsigned long long h = pair_slot(p, e.key, &seen);
   if (h == ~0ULL) return;
   p.pairs[h].acc = e.acc;  // keys are unique in the old table: no other thread touches this slot
+}
+
+// ---- multi-GPU exchange: the table's records grouped by destination rank, hash(key) mod n_parts ----
+__device__ __forceinline__ uint32_t part_of(unsigned long long key, uint32_t n_parts) {
+  return (uint32_t)(mix64(key) >> 40) % n_parts;
+}
+constexpr int kMaxParts = 64;
+
+__global__ void __launch_bounds__(256) k_partition_count(const PairEntry* tab, unsigned long long cap, uint32_t n_parts,
+                                                         unsigned long long* counts) {
+  __shared__ uint32_t c[kMaxParts];
+  if (threadIdx.x < kMaxParts) c[threadIdx.x] = 0;
+  __syncthreads();
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long key = tab[i].key;
+    if (key != 0ULL) atomicAdd(&c[part_of(key, n_parts)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts && c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)c[threadIdx.x]);
+}
+
+// cursors[part] starts at the part's first output index; one atomic per group of lanes with the same destination
+__global__ void __launch_bounds__(256) k_partition_scatter(const PairEntry* tab, unsigned long long cap, uint32_t n_parts,
+                                                           unsigned long long* cursors, citam_pair* out,
+                                                           unsigned long long out_cap) {
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < cap;
+       i0 += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = i0 + threadIdx.x;
+    PairEntry e; e.key = 0ULL; e.acc = 0ULL;
+    if (i < cap) e = tab[i];
+    const uint32_t part = e.key != 0ULL ? part_of(e.key, n_parts) : 0xffffffffu - (threadIdx.x & 31);
+    const unsigned peers = __match_any_sync(0xffffffffu, part);
+    if (e.key == 0ULL) continue;
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&cursors[part], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1u));
+    if (base < out_cap) out[base] = entry_to_pair(e.key, e.acc);
+  }
 }
 
 // pass 1: per-agent event sums and "has a pair" flags; pass 2: reduce over agents
@@ -1143,18 +1291,25 @@ __global__ void k_stats_agents(const uint32_t* agent_nev, const uint32_t* agent_
   }
 }
 
-__global__ void k_merge_pairs(Params p, const citam_pair* in, unsigned long long n) {
+// Records of another engine (rank) into this table.  Only the pair table is touched: per-agent
+// contact seconds are reduced separately (all-reduce of the counters), see the header.
+__global__ void k_merge_pairs(Params p, const citam_pair* in, unsigned long long n, int* bad) {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   citam_pair r = in[i];
-  pair_upsert(p, r.a1, r.a2, r.first_step, r.duration, r.n_events);
+  if (r.a1 >= r.a2 || r.a2 >= (uint32_t)p.N || r.duration > 0xffffffULL || r.n_events > 0xffffu) { atomicOr(bad, 1); return; }
+  unsigned long long old;
+  unsigned long long h = pair_slot(p, ((unsigned long long)r.a1 << 32) | r.a2, &old);
+  if (h == ~0ULL) return;
+  pair_apply_acc(p, h, old, r.first_step > 0xFFFFFFu ? NO_STEP : r.first_step, r.duration, r.n_events);
 }
 
 __global__ void k_merge_coords(Params p, const citam_coord* in, unsigned long long n) {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   citam_coord r = in[i];
-  coord_upsert(p, r.floor, r.sx, r.sy, r.count);
+  const FloorDev& fd = p.floors[r.floor];
+  coord_upsert_rel(p, r.floor, r.sx - 2 * fd.minx, r.sy - 2 * fd.miny, r.count);
 }
 
 __global__ void k_repack_segments(const citam_segment* in, long long n, int4* out) {
@@ -1205,13 +1360,17 @@ struct citam_engine {
 
   PairEntry* pairs = nullptr;
   unsigned long long pair_cap = 0;
-  bool pair_auto = false;  // capacity chosen by the library: grow when half full
+  bool pair_auto = false;  // capacity chosen by the library: grown when a quarter full
+  DevCounters* snap_h = nullptr;  // pinned: the counters as of the previous chunk (occupancy check without a stall)
+  cudaEvent_t ev_snap = nullptr;
+  bool snap_pending = false;
   unsigned long long* hist = nullptr;  // dense coordinate histogram (all floors), NULL = hashed
   long long hist_total = 0;
-  int32_t range_begin = -1;
-  CoordEntry* coords = nullptr;
+  int32_t range_begin = -1, range_end = INT_MAX;
+  uint32_t max_step = 0;  // largest step any accumulated record can carry (sort key width)
+  CoordEntry* coords = nullptr;  // allocated only when the dense histogram is not in use
   unsigned long long coord_cap = 0;
-  citam_contact* log = nullptr;
+  uint4* log = nullptr;
   unsigned long long log_cap = 0;
   ContactRec* cbuf = nullptr;  // the current one of cbuf_buf
   ContactRec* cbuf_buf[2] = {nullptr, nullptr};
@@ -1220,6 +1379,7 @@ struct citam_engine {
   unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
   DevCounters* ctr_d = nullptr;
+  int* flag_d = nullptr;  // scratch word for device-side validation
 
   // Calculator.run entry: previous explicit state row
   int4* prev = nullptr;
@@ -1255,6 +1415,12 @@ static unsigned long long next_pow2(unsigned long long v) {
   unsigned long long p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+
+static int bits_of(unsigned long long v) {
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b;
 }
 
 struct Timed {
@@ -1322,11 +1488,16 @@ static unsigned long long pairs_used(const DevCounters& c) {
 static Params make_params(citam_engine* e) {
   Params p{};
   p.N = e->N; p.F = e->F; p.cell = e->cell; p.total_cells = e->total_cells; p.cells_stride = e->cells_stride;
-  p.D = e->D; p.s_max = e->s_max; p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
+  p.cell_magic = e->cell > 1 ? (uint32_t)((1ULL << 32) / (unsigned)e->cell) + 1u : 0u;
+  p.D = e->D;
+  p.s_lim = (unsigned long long)(e->s_max + 1);
+  p.d_lim = e->s_max < 0 ? 0u : (uint32_t)std::min<long long>(65535, (long long)std::floor(std::sqrt((double)e->s_max)) + 1);
+  p.floors = e->floors_d; p.segs = e->segs_d; p.seg_off = e->seg_off_d;
   p.window = (e->have_itin && !e->window_dirty && !e->explicit_states) ? e->window_d : nullptr;
   p.rec = e->rec; p.cells = e->cells;
   p.sorted = e->sorted; p.pairs = e->pairs; p.pair_mask = e->pair_cap - 1;
-  p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist; p.range_begin = e->range_begin;
+  p.coords = e->coords; p.coord_mask = e->coord_cap - 1; p.hist = e->hist;
+  p.range_begin = e->range_begin; p.range_end = e->range_end;
   p.log = e->log; p.log_cap = e->log_cap;
   p.cbuf = (e->log_cap || !e->hist) ? nullptr : e->cbuf; p.cbuf_sub_cap = e->cbuf_cap / kSubBuffers;
   p.cbuf_count = e->ctr_d->cbuf_count[e->cur];
@@ -1384,6 +1555,10 @@ static int ensure_ready(citam_engine* e, int want_steps) {
         e->hist_total = tot;
       }
     }
+    if (!e->hist && !e->coords) {  // the hashed histogram exists only when the dense one does not
+      CK(cudaMalloc(&e->coords, sizeof(CoordEntry) * e->coord_cap));
+      CK(cudaMemsetAsync(e->coords, 0, sizeof(CoordEntry) * e->coord_cap, e->stream));
+    }
     CK(cudaMemcpyAsync(e->floors_d, e->floors_h.data(), sizeof(FloorDev) * e->F, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->floors_dirty = false;
@@ -1413,8 +1588,7 @@ static int ensure_ready(citam_engine* e, int want_steps) {
 
 static int pick_chunk(citam_engine* e, int steps) {
   if (e->cfg.steps_per_chunk > 0) return std::min(std::min(steps, e->cfg.steps_per_chunk), kMaxChunk);
-  // ~64M agent-steps per launch group (2 GiB of per-step records), bounded by 1 GiB of histogram
-  // rows and by the 8-bit stationary-run counter
+  // ~64M agent-steps per launch group (3.3 GiB of per-step records), bounded by 1 GiB of histogram rows
   long long by_agents = std::max(1LL, (64LL << 20) / std::max(1, e->N));
   long long by_cells = std::max(1LL, (1LL << 28) / std::max(4, e->cells_stride));
   long long s = std::min(by_agents, by_cells);
@@ -1440,26 +1614,31 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
       k_scan_add<<<dim3(parts - 1, rows), 256, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
                                                                e->part_sums);
   }
+  const bool agg = p.chg_count != nullptr;
+  // the first step of a range is evaluated in full (k_pairs); every other step through its changed agents
+  const int row0 = (t_begin == e->range_begin) ? 1 : 0;
   {
     Timed tm(e, CITAM_K_SCATTER);
     dim3 g((e->N + 255) / 256, rows);
     k_scatter<<<g, 256, 0, e->stream>>>(p, rows, t_begin);
-    if (p.chg_count != nullptr && rows > 1) {
+    if (agg && rows > row0) {
       e->launches++;
-      dim3 g3((unsigned)std::min(296, std::max(1, (e->N + 255) / 256)), rows - 1);
-      k_select_changed<<<g3, 256, 0, e->stream>>>(p, rows);
+      dim3 g3((unsigned)std::min(296, std::max(1, (e->N + 255) / 256)), rows - row0);
+      k_select_changed<<<g3, 256, 0, e->stream>>>(p, row0, rows);
     }
   }
   {
     Timed tm(e, CITAM_K_PAIRS);
-    const bool agg = p.chg_count != nullptr;
-    // first step of the chunk (or every step when the log is on): all located agents
-    dim3 g((e->N + 255) / 256, agg ? 1 : rows);
-    k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0);
-    if (agg && rows > 1) {
-      e->launches++;
-      dim3 g2((unsigned)std::min(592, std::max(1, (e->N + 255) / 256)), rows - 1);
-      k_pairs_changed<<<g2, 256, 0, e->stream>>>(p, t_begin, rows);
+    bool launched = false;
+    if (!agg || row0 == 1) {
+      dim3 g((e->N + 255) / 256, agg ? 1 : rows);
+      k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0);
+      launched = true;
+    }
+    if (agg && rows > row0) {
+      if (launched) e->launches++;
+      dim3 g2((unsigned)std::min(592, std::max(1, (e->N + 255) / 256)), rows - row0);
+      k_pairs_changed<<<g2, 256, 0, e->stream>>>(p, t_begin, row0, rows);
     }
   }
   if (p.cbuf != nullptr) {
@@ -1491,23 +1670,73 @@ static int check_overflow(citam_engine* e) {
   return CITAM_OK;
 }
 
-extern "C" {
+// Replace the pair table by one of `ncap` slots holding the same entries.  The caller has joined the side stream.
+static int rehash_pairs(citam_engine* e, unsigned long long ncap) {
+  PairEntry* np = nullptr;
+  if (cudaMalloc(&np, sizeof(PairEntry) * ncap) != cudaSuccess) {
+    cudaGetLastError();
+    return CITAM_ERR_CAPACITY;  // not fatal for the callers that grow opportunistically
+  }
+  CK(cudaMemsetAsync(np, 0, sizeof(PairEntry) * ncap, e->stream));
+  PairEntry* old = e->pairs;
+  unsigned long long ocap = e->pair_cap;
+  e->pairs = np; e->pair_cap = ncap;
+  CK(cudaMemsetAsync(&e->ctr_d->pair_used, 0, sizeof(unsigned long long), e->stream));
+  CK(cudaMemsetAsync(e->ctr_d->pair_used_sub, 0, sizeof(unsigned long long) * kSubBuffers * kCounterStride, e->stream));
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_MISC);
+    k_rehash_pairs<<<(unsigned)((ocap + 255) / 256), 256, 0, e->stream>>>(p, old, ocap);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(old);
+  return CITAM_OK;
+}
 
-int citam_abi_version(void) { return CITAM_ABI_VERSION; }
-const char* citam_last_error(void) { return g_err.c_str(); }
+// Library-chosen pair capacity: the table is doubled until it is at most a quarter full.  Between
+// chunks the occupancy comes from an asynchronous snapshot of the counters taken one chunk earlier
+// (no stall: k_accumulate keeps overlapping the next chunk's build); `now` forces a fresh read.
+static int maybe_grow_pairs(citam_engine* e, bool now) {
+  if (!e->pair_auto) return CITAM_OK;
+  unsigned long long used = 0;
+  bool have = false, overflowed = false;
+  if (now) {
+    int rcj = join_side_stream(e);
+    if (rcj) return rcj;
+    if (e->snap_pending) CK(cudaEventSynchronize(e->ev_snap));  // an older snapshot must not land after this one
+    CK(cudaMemcpyAsync(e->snap_h, e->ctr_d, sizeof(DevCounters), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->snap_pending = false;
+    have = true;
+  } else if (e->snap_pending && cudaEventQuery(e->ev_snap) == cudaSuccess) {
+    e->snap_pending = false;
+    have = true;
+  }
+  if (have) {
+    used = pairs_used(*e->snap_h);
+    overflowed = (e->snap_h->overflow & OVF_PAIR) != 0;
+    if (used * 4 > e->pair_cap && !overflowed) {
+      int rcj = join_side_stream(e);
+      if (rcj) return rcj;
+      unsigned long long ncap = e->pair_cap;
+      while (used * 4 > ncap) ncap *= 2;
+      int rc = rehash_pairs(e, ncap);
+      if (rc == CITAM_ERR_CAPACITY) e->pair_auto = false;  // out of memory: keep the table, overflow is reported if it comes
+      else if (rc) return rc;
+    }
+  }
+  if (!now && !e->snap_pending) {
+    // counters as they are once everything enqueued so far on both streams is done
+    cudaStream_t s = e->applied_pending[e->cur] ? e->stream2 : e->stream;
+    CK(cudaMemcpyAsync(e->snap_h, e->ctr_d, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(e->ev_snap, s));
+    e->snap_pending = true;
+  }
+  return CITAM_OK;
+}
 
-int citam_create(const citam_config* cfg, citam_engine** out) {
-  if (!cfg || !out) return fail(CITAM_ERR_INVALID, "null argument");
-  if (cfg->n_agents <= 0 || cfg->n_floors <= 0 || cfg->n_floors > kMaxFloors)
-    return fail(CITAM_ERR_INVALID, "n_agents must be > 0 and n_floors in 1..63");
-  if (!(cfg->contact_distance >= 0.0) || cfg->contact_distance > 1e6)
-    return fail(CITAM_ERR_INVALID, "contact_distance out of range");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(CITAM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
-  if (cfg->device < 0 || cfg->device >= ndev) return fail(CITAM_ERR_INVALID, "device %d out of range", cfg->device);
-  CK(cudaSetDevice(cfg->device));
-  citam_engine* e = new citam_engine();
+static int create_impl(citam_engine* e, const citam_config* cfg) {
   if (const char* g = getenv("CITAM_ACC_BLOCKS")) e->acc_blocks = std::max(1, atoi(g));
   e->cfg = *cfg;
   e->device = cfg->device;
@@ -1526,34 +1755,88 @@ int citam_create(const citam_config* cfg, citam_engine** out) {
   e->pair_cap = next_pow2(cfg->pair_capacity ? cfg->pair_capacity : std::min<unsigned long long>(1ULL << 28, std::max<unsigned long long>(1ULL << 22, 256ULL * e->N)));
   e->coord_cap = next_pow2(cfg->coord_capacity ? cfg->coord_capacity : std::min<unsigned long long>(1ULL << 27, std::max<unsigned long long>(1ULL << 20, 64ULL * e->N)));
   e->log_cap = cfg->log_capacity;
-  *out = e;
   size_t n = (size_t)e->N;
   CK(cudaMalloc(&e->floors_d, sizeof(FloorDev) * e->F));
   CK(cudaMalloc(&e->pairs, sizeof(PairEntry) * e->pair_cap));
-  CK(cudaMalloc(&e->coords, sizeof(CoordEntry) * e->coord_cap));
-  if (e->log_cap) CK(cudaMalloc(&e->log, sizeof(citam_contact) * e->log_cap));
+  if (e->log_cap) CK(cudaMalloc(&e->log, sizeof(uint4) * e->log_cap));
   CK(cudaMalloc(&e->agent_dur, sizeof(unsigned long long) * n));
   CK(cudaMalloc(&e->agent_nev, sizeof(uint32_t) * n));
   CK(cudaMalloc(&e->agent_has, sizeof(uint32_t) * n));
   CK(cudaMalloc(&e->ctr_d, sizeof(DevCounters)));
+  CK(cudaMalloc(&e->flag_d, sizeof(int)));
   CK(cudaMalloc(&e->prev, sizeof(int4) * n));
   CK(cudaMalloc(&e->states_d, sizeof(citam_agent_state) * n));
+  CK(cudaMallocHost(&e->snap_h, sizeof(DevCounters)));
+  CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   for (int b = 0; b < 2; ++b) {
     CK(cudaEventCreateWithFlags(&e->ev_built[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_applied[b], cudaEventDisableTiming));
   }
   {
-    int* bad_d = nullptr;
     int bad = 1;
-    CK(cudaMalloc(&bad_d, sizeof(int)));
-    k_check_s_max<<<1, 1, 0, e->stream>>>(e->D, e->s_max, bad_d);
-    CK(cudaMemcpyAsync(&bad, bad_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    k_check_s_max<<<1, 1, 0, e->stream>>>(e->D, e->s_max, e->flag_d);
+    CK(cudaMemcpyAsync(&bad, e->flag_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(bad_d);
     if (bad) return fail(CITAM_ERR_CUDA, "integer distance threshold %lld disagrees with the float64 predicate", e->s_max);
   }
   return citam_reset(e);
+}
+
+// Device sort of `n` 16-byte records in `a` (scratch `b`); *res points at the sorted copy.
+template <typename KeyFn>
+static int device_sort(citam_engine* e, uint4* a, uint4* b, unsigned long long n, const rsort::Pass* passes, int np,
+                       KeyFn key, uint4** res) {
+  *res = a;
+  if (n < 2 || np == 0) return CITAM_OK;
+  if (n >= (1ULL << 32)) return fail(CITAM_ERR_CAPACITY, "device sort holds fewer than 2^32 records");
+  uint32_t* ws = nullptr;
+  CK(cudaMalloc(&ws, rsort::workspace_bytes(n)));
+  cudaError_t err;
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    err = rsort::sort(a, b, n, passes, np, ws, e->stream, key, res, &e->launches);
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(ws);
+  if (err != cudaSuccess) return fail(CITAM_ERR_CUDA, "device sort failed: %s", cudaGetErrorString(err));
+  return CITAM_OK;
+}
+
+// One flag word, set by a device-side check: returns its value (and clears it).
+static int read_flag(citam_engine* e, int* v) {
+  CK(cudaMemcpyAsync(v, e->flag_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return CITAM_OK;
+}
+
+extern "C" {
+
+int citam_abi_version(void) { return CITAM_ABI_VERSION; }
+const char* citam_last_error(void) { return g_err.c_str(); }
+
+int citam_create(const citam_config* cfg, citam_engine** out) {
+  if (!cfg || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_agents <= 0 || cfg->n_floors <= 0 || cfg->n_floors > kMaxFloors)
+    return fail(CITAM_ERR_INVALID, "n_agents must be > 0 and n_floors in 1..63");
+  if (!(cfg->contact_distance >= 0.0) || cfg->contact_distance > 1e6)
+    return fail(CITAM_ERR_INVALID, "contact_distance out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(CITAM_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(CITAM_ERR_INVALID, "device %d out of range", cfg->device);
+  CK(cudaSetDevice(cfg->device));
+  citam_engine* e = new citam_engine();
+  int rc = create_impl(e, cfg);
+  if (rc) {  // nothing of a half-built engine survives
+    std::string msg = g_err;
+    citam_destroy(e);
+    g_err = msg;
+    return rc;
+  }
+  *out = e;
+  return CITAM_OK;
 }
 
 void citam_destroy(citam_engine* e) {
@@ -1565,12 +1848,15 @@ void citam_destroy(citam_engine* e) {
   free_chunk(e);
   if (e->stream2) cudaStreamDestroy(e->stream2);
   for (int b = 0; b < 2; ++b) { if (e->ev_built[b]) cudaEventDestroy(e->ev_built[b]); if (e->ev_applied[b]) cudaEventDestroy(e->ev_applied[b]); }
+  if (e->ev_snap) cudaEventDestroy(e->ev_snap);
+  if (e->snap_h) cudaFreeHost(e->snap_h);
   for (auto p : e->lut_d) cudaFree(p);
   for (auto p : e->adj_d) cudaFree(p);
   cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->window_d); cudaFree(e->pairs);
   cudaFree(e->coords); cudaFree(e->hist);
   cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->ctr_d);
-  cudaFree(e->prev); cudaFree(e->states_d);
+  cudaFree(e->flag_d); cudaFree(e->prev); cudaFree(e->states_d);
+  cudaGetLastError();
   delete e;
 }
 
@@ -1583,19 +1869,36 @@ int citam_set_stream(citam_engine* e, void* s) {
 int citam_reset(citam_engine* e) {
   if (!e) return fail(CITAM_ERR_INVALID, "null engine");
   CK(cudaSetDevice(e->device));
+  int rc = join_side_stream(e);
+  if (rc) return rc;
   CK(cudaMemsetAsync(e->pairs, 0, sizeof(PairEntry) * e->pair_cap, e->stream));
-  CK(cudaMemsetAsync(e->coords, 0, sizeof(CoordEntry) * e->coord_cap, e->stream));
+  if (e->coords) CK(cudaMemsetAsync(e->coords, 0, sizeof(CoordEntry) * e->coord_cap, e->stream));
   if (e->hist) CK(cudaMemsetAsync(e->hist, 0, sizeof(unsigned long long) * (size_t)e->hist_total, e->stream));
   CK(cudaMemsetAsync(e->agent_dur, 0, sizeof(unsigned long long) * (size_t)e->N, e->stream));
   CK(cudaMemsetAsync(e->ctr_d, 0, sizeof(DevCounters), e->stream));
+  e->snap_pending = false;
   e->prev_step = LLONG_MIN;
   e->agent_steps = 0;
+  e->max_step = 0;
+  return CITAM_OK;
+}
+
+int citam_clear_pairs(citam_engine* e) {
+  if (!e) return fail(CITAM_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->device));
+  int rc = join_side_stream(e);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(e->pairs, 0, sizeof(PairEntry) * e->pair_cap, e->stream));
+  CK(cudaMemsetAsync(&e->ctr_d->pair_used, 0, sizeof(unsigned long long), e->stream));
+  CK(cudaMemsetAsync(e->ctr_d->pair_used_sub, 0, sizeof(unsigned long long) * kSubBuffers * kCounterStride, e->stream));
+  e->snap_pending = false;
   return CITAM_OK;
 }
 
 static int install_lut(citam_engine* e, int floor, int minx, int miny, int W, int H, int n_spaces) {
   if (floor < 0 || floor >= e->F) return fail(CITAM_ERR_INVALID, "floor %d out of range", floor);
-  if (W <= 0 || H <= 0 || (long long)W * H > (1LL << 31)) return fail(CITAM_ERR_INVALID, "bad lattice %dx%d", W, H);
+  if (W <= 0 || H <= 0 || W > 65536 || H > 65536 || (long long)W * H > (1LL << 31))
+    return fail(CITAM_ERR_INVALID, "bad lattice %dx%d (sides <= 65536, at most 2^31 points)", W, H);
   if (n_spaces < 0 || n_spaces > 32767) return fail(CITAM_ERR_INVALID, "n_spaces must be <= 32767");
   CK(cudaSetDevice(e->device));
   cudaFree(e->lut_d[floor]);
@@ -1682,7 +1985,7 @@ int citam_set_floor_adjacency(citam_engine* e, int32_t floor, int32_t n_spaces, 
 
 int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_segment* segs, int64_t n_segs) {
   if (!e || !seg_off || (n_segs > 0 && !segs)) return fail(CITAM_ERR_INVALID, "null argument");
-  if (seg_off[0] != 0 || seg_off[e->N] != n_segs) return fail(CITAM_ERR_INVALID, "seg_off must run from 0 to n_segs");
+  if (n_segs < 0 || seg_off[0] != 0 || seg_off[e->N] != n_segs) return fail(CITAM_ERR_INVALID, "seg_off must run from 0 to n_segs");
   CK(cudaSetDevice(e->device));
   e->have_itin = false;
   // buffers are kept between calls (time-block streaming reloads a slice per block)
@@ -1696,60 +1999,36 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
   }
   if (!e->seg_off_d) CK(cudaMalloc(&e->seg_off_d, sizeof(long long) * ((size_t)e->N + 1)));
   citam_segment* raw = e->raw_d;
+  CK(cudaMemsetAsync(e->flag_d, 0, sizeof(int), e->stream));
   CK(cudaMemcpyAsync(e->seg_off_d, seg_off, sizeof(long long) * ((size_t)e->N + 1), cudaMemcpyHostToDevice, e->stream));
-  if (n_segs) {
-    CK(cudaMemcpyAsync(raw, segs, sizeof(citam_segment) * n_segs, cudaMemcpyHostToDevice, e->stream));
+  if (n_segs) CK(cudaMemcpyAsync(raw, segs, sizeof(citam_segment) * n_segs, cudaMemcpyHostToDevice, e->stream));
+  {
+    // the documented limits, checked on the device copy (no host pass over 10^7-10^8 records)
     Timed tm(e, CITAM_K_MISC);
-    k_repack_segments<<<(unsigned)((n_segs + 255) / 256), 256, 0, e->stream>>>(raw, n_segs, e->segs_d);
+    k_validate_segments<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->seg_off_d, raw, n_segs, e->N, e->flag_d);
+    if (n_segs) k_repack_segments<<<(unsigned)((n_segs + 255) / 256), 256, 0, e->stream>>>(raw, n_segs, e->segs_d);
   }
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(e->stream));  // the caller's host buffers are free to change again
+  int bad = 0;
+  int rc = read_flag(e, &bad);  // also: the caller's host buffers are free to change again
+  if (rc) return rc;
+  if (bad)
+    return fail(CITAM_ERR_INVALID, "itinerary store violates the documented limits:%s%s%s%s%s",
+                (bad & 1) ? " seg_off is not non-decreasing inside [0, n_segs];" : "",
+                (bad & 2) ? " t0 must increase strictly per agent and stay in [0, 2^24 - 3];" : "",
+                (bad & 4) ? " floor must be in 0..62;" : "",
+                (bad & 16) ? " |coordinates| must be below 2^26;" : "",
+                (bad & 8) ? " an agent's last segment must have zero velocity (the sticky tail);" : "");
   e->n_segs = n_segs;
   e->have_itin = true;
   e->window_dirty = true;
   return CITAM_OK;
 }
 
-// Library-chosen pair capacity: double the table once it is half full (checked between chunks).
-static int maybe_grow_pairs(citam_engine* e) {
-  if (!e->pair_auto) return CITAM_OK;
-  {  // the table is about to be read (and perhaps replaced): no accumulation may be in flight
-    int rcj = join_side_stream(e);
-    if (rcj) return rcj;
-  }
-  DevCounters c;
-  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  while (pairs_used(c) * 2 > e->pair_cap && !(c.overflow & OVF_PAIR)) {
-    unsigned long long ncap = e->pair_cap * 2;
-    PairEntry* np = nullptr;
-    if (cudaMalloc(&np, sizeof(PairEntry) * ncap) != cudaSuccess) {
-      cudaGetLastError();
-      e->pair_auto = false;  // out of memory: keep the table, overflow is reported if it comes
-      return CITAM_OK;
-    }
-    CK(cudaMemsetAsync(np, 0, sizeof(PairEntry) * ncap, e->stream));
-    PairEntry* old = e->pairs;
-    unsigned long long ocap = e->pair_cap;
-    e->pairs = np; e->pair_cap = ncap;
-    CK(cudaMemsetAsync(&e->ctr_d->pair_used, 0, sizeof(unsigned long long), e->stream));
-    CK(cudaMemsetAsync(e->ctr_d->pair_used_sub, 0, sizeof(c.pair_used_sub), e->stream));
-    Params p = make_params(e);
-    {
-      Timed tm(e, CITAM_K_MISC);
-      k_rehash_pairs<<<(unsigned)((ocap + 255) / 256), 256, 0, e->stream>>>(p, old, ocap);
-    }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(e->stream));
-    cudaFree(old);
-  }
-  return CITAM_OK;
-}
-
 int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
   if (!e) return fail(CITAM_ERR_INVALID, "null engine");
   if (!e->have_itin) return fail(CITAM_ERR_STATE, "citam_run before citam_load_itineraries");
-  if (t_begin < 0 || t_end < t_begin || t_end > (1 << 24)) return fail(CITAM_ERR_INVALID, "bad step range");
+  if (t_begin < 0 || t_end < t_begin || t_end > (1 << 24) - 1) return fail(CITAM_ERR_INVALID, "bad step range (steps < 2^24 - 1)");
   if (t_end == t_begin) return CITAM_OK;
   CK(cudaSetDevice(e->device));
   int rc = ensure_ready(e, 1);  // uploads floor descriptors so pick_chunk sees the grid
@@ -1767,38 +2046,46 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     CK(cudaGetLastError());
     e->window_dirty = false;
   }
-  e->range_begin = t_begin;
-  for (int tb = t_begin; tb < t_end; tb += S) {
-    rc = begin_chunk(e);
-    if (rc) return rc;
-    Params p = make_params(e);
-    int steps = std::min(S, t_end - tb);
-    int rows = steps + 1;  // + halo row for step tb-1
-    CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride * steps, e->stream));
-    CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
-    {
-      Timed tm(e, CITAM_K_EXPAND_BIN);
-      // one thread walks an agent through `rpt` consecutive steps: as many as possible (one
-      // segment search per agent) while the launch still fills the machine
-      int rpt = 16;
-      while (rpt < rows && (long long)e->N * ((rows + 2 * rpt - 1) / (2 * rpt)) >= 600000) rpt *= 2;
-      dim3 g((e->N + 127) / 128, (rows + rpt - 1) / rpt);
-      k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb - 1, rows, 1, rpt);
+  e->max_step = std::max<uint32_t>(e->max_step, (uint32_t)t_end);
+  // a contact run is one table update however many chunks it crosses; runs are clipped to the range
+  // (and to 2^20 steps, the width of the run field: longer ranges are processed as several)
+  for (int rb = t_begin; rb < t_end; rb += (1 << kMaxRunLog2)) {
+    e->range_begin = rb;
+    e->range_end = std::min(t_end, rb + (1 << kMaxRunLog2));
+    for (int tb = rb; tb < e->range_end; tb += S) {
+      rc = begin_chunk(e);
+      if (rc) return rc;
+      Params p = make_params(e);
+      int steps = std::min(S, e->range_end - tb);
+      int rows = steps + 1;  // + halo row for step tb-1
+      CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride * steps, e->stream));
+      CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
+      {
+        Timed tm(e, CITAM_K_EXPAND_BIN);
+        // one thread walks an agent through `rpt` consecutive steps: as many as possible (one
+        // segment search per agent) while the launch still fills the machine
+        int rpt = 16;
+        while (rpt < rows && (long long)e->N * ((rows + 2 * rpt - 1) / (2 * rpt)) >= 600000) rpt *= 2;
+        dim3 g((e->N + 127) / 128, (rows + rpt - 1) / rpt);
+        k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb - 1, rows, 1, rpt);
+      }
+      CK(cudaGetLastError());
+      rc = run_sorted_stages(e, tb, steps);
+      if (rc) return rc;
+      e->agent_steps += (unsigned long long)steps * e->N;
+      rc = maybe_grow_pairs(e, false);
+      if (rc) return rc;
     }
-    CK(cudaGetLastError());
-    rc = run_sorted_stages(e, tb, steps);
-    if (rc) return rc;
-    e->agent_steps += (unsigned long long)steps * e->N;
-    rc = maybe_grow_pairs(e);
-    if (rc) return rc;
   }
   e->prev_step = LLONG_MIN;
-  return join_side_stream(e);
+  rc = join_side_stream(e);
+  if (rc) return rc;
+  return maybe_grow_pairs(e, true);
 }
 
 int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* states) {
   if (!e || !states) return fail(CITAM_ERR_INVALID, "null argument");
-  if (step < 0) return fail(CITAM_ERR_INVALID, "negative step");
+  if (step < 0 || step > (1 << 24) - 2) return fail(CITAM_ERR_INVALID, "step out of range");
   CK(cudaSetDevice(e->device));
   int rc = ensure_ready(e, 1);
   if (rc) return rc;
@@ -1813,15 +2100,16 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   } else {
     k_fill_inactive<<<g, 256, 0, e->stream>>>(e->rec, e->N);
     e->launches++;
+    e->range_begin = step;
   }
-  k_states_to_rec<<<g, 256, 0, e->stream>>>(e->states_d, e->N, e->rec + n);
-  e->launches++;
-  if (e->prev_step != (long long)step - 1) e->range_begin = step;
+  e->range_end = INT_MAX;  // explicit states: every agent's `until` is step + 1
+  e->max_step = std::max<uint32_t>(e->max_step, (uint32_t)step + 1);
   CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
+  CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32, e->stream));
   Params p = make_params(e);
   {
     Timed tm(e, CITAM_K_EXPAND_BIN);
-    k_bin_states<<<dim3(g, 1), 256, 0, e->stream>>>(p, 2);
+    k_states_to_rec<<<g, 256, 0, e->stream>>>(p, e->states_d, e->rec + n, step, 1);
   }
   CK(cudaGetLastError());
   rc = run_sorted_stages(e, step, 1);
@@ -1831,7 +2119,7 @@ int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* st
   e->agent_steps += e->N;
   rc = join_side_stream(e);
   if (rc) return rc;
-  rc = maybe_grow_pairs(e);
+  rc = maybe_grow_pairs(e, true);
   if (rc) return rc;
   return check_overflow(e);
 }
@@ -1842,12 +2130,14 @@ int citam_states_at(citam_engine* e, int32_t step, citam_agent_state* out) {
   CK(cudaSetDevice(e->device));
   int rc = ensure_ready(e, 1);
   if (rc) return rc;
+  rc = join_side_stream(e);
+  if (rc) return rc;
   Params p = make_params(e);
   {
     Timed tm(e, CITAM_K_MISC);
     dim3 g((e->N + 127) / 128, 1);
     k_expand_bin<<<g, 128, 0, e->stream>>>(p, step, 1, 0, 16);
-    k_rec_to_states<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->rec, e->N, e->states_d);
+    k_rec_to_states<<<(e->N + 255) / 256, 256, 0, e->stream>>>(p, e->rec, e->N, e->states_d);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, e->states_d, sizeof(citam_agent_state) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
@@ -1864,6 +2154,8 @@ int citam_states_range(citam_engine* e, int32_t t_begin, int32_t t_end, citam_ag
   CK(cudaSetDevice(e->device));
   int rc = ensure_ready(e, 1);
   if (rc) return rc;
+  rc = join_side_stream(e);
+  if (rc) return rc;
   const int rows_max = std::max(1, std::min(e->S + 1, t_end - t_begin));
   size_t n = (size_t)e->N;
   citam_agent_state* tmp = nullptr;
@@ -1877,7 +2169,7 @@ int citam_states_range(citam_engine* e, int32_t t_begin, int32_t t_end, citam_ag
       dim3 g((e->N + 127) / 128, (rows + kRowsPerThread - 1) / kRowsPerThread);
       k_expand_bin<<<g, 128, 0, e->stream>>>(p, tb, rows, 0, kRowsPerThread);
       size_t tot = n * rows;
-      k_rec_to_states<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->rec, (long long)tot, tmp);
+      k_rec_to_states<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(p, e->rec, (long long)tot, tmp);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out + (size_t)(tb - t_begin) * n, tmp, sizeof(citam_agent_state) * n * rows, cudaMemcpyDeviceToHost, e->stream));
@@ -1907,6 +2199,7 @@ int citam_get_counters(citam_engine* e, citam_counters* out) {
 }
 
 int citam_pair_count(citam_engine* e, uint64_t* n) {
+  if (!n) return fail(CITAM_ERR_INVALID, "null argument");
   citam_counters c;
   int rc = citam_get_counters(e, &c);
   if (rc) return rc;
@@ -1933,47 +2226,82 @@ static int dense_coord_count(citam_engine* e, uint64_t* n) {
 int citam_coord_count(citam_engine* e, uint64_t* n) {
   if (!e || !n) return fail(CITAM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->device));
+  int rc = ensure_ready(e, 1);
+  if (rc) return rc;
   if (e->hist) return dense_coord_count(e, n);
   citam_counters c;
-  int rc = citam_get_counters(e, &c);
+  rc = citam_get_counters(e, &c);
   if (rc) return rc;
   *n = c.coord_slots_used;
   return CITAM_OK;
 }
 
+// The pair table in the reference's row order -- first contact step, then (a1, a2): dict insertion
+// order of contacts.py:135-142 with pairs of one step visited row-major
+// (close_contacts_calculator.py:104-124) -- into a DEVICE buffer.
+int citam_export_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t capacity, uint64_t* n) {
+  if (!e || !n || (capacity && !out_device)) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  uint64_t have = 0;
+  int rc = citam_pair_count(e, &have);
+  if (rc) return rc;
+  *n = have;
+  if (have == 0) return CITAM_OK;
+  if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu pairs, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
+  PairEntry *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, sizeof(PairEntry) * have) != cudaSuccess || cudaMalloc(&b, sizeof(PairEntry) * have) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(a);
+    return fail(CITAM_ERR_CUDA, "out of device memory for the export of %llu pairs", (unsigned long long)have);
+  }
+  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_compact_entries<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, a, have, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  rsort::Pass passes[12];
+  int np = 0;
+  const int ab = bits_of((unsigned long long)e->N - 1);
+  np += rsort::plan_word(passes + np, 0, ab);
+  np += rsort::plan_word(passes + np, 1, ab);
+  np += rsort::plan_word(passes + np, 2, std::min(24, bits_of(e->max_step)));
+  uint4* res = nullptr;
+  rc = device_sort(e, reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(b), have, passes, np, PairKey(), &res);
+  if (rc == CITAM_OK) {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_entries_to_pairs<<<(unsigned)((have + 255) / 256), 256, 0, e->stream>>>(reinterpret_cast<PairEntry*>(res), have, out_device);
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(CITAM_ERR_CUDA, "pair export failed: %s", cudaGetErrorString(err));
+  }
+  cudaFree(a); cudaFree(b);
+  return rc;
+}
+
 int citam_export_pairs(citam_engine* e, citam_pair* out, uint64_t capacity, uint64_t* n) {
   if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
-  int rc = check_overflow(e);
-  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
   uint64_t have = 0;
-  rc = citam_pair_count(e, &have);
+  int rc = citam_pair_count(e, &have);
   if (rc) return rc;
   *n = have;
   if (have == 0) return CITAM_OK;
   if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu pairs, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
   citam_pair* tmp = nullptr;
   CK(cudaMalloc(&tmp, sizeof(citam_pair) * have));
-  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
-  {
-    Timed tm(e, CITAM_K_FINALIZE);
-    k_compact_pairs<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, tmp, have, e->ctr_d);
+  rc = citam_export_pairs_device(e, tmp, have, n);
+  if (rc == CITAM_OK) {
+    cudaError_t err = cudaMemcpyAsync(out, tmp, sizeof(citam_pair) * have, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(CITAM_ERR_CUDA, "pair export failed: %s", cudaGetErrorString(err));
   }
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, tmp, sizeof(citam_pair) * have, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
   cudaFree(tmp);
-  // first-contact order = dict insertion order of the reference (contacts.py:135-142;
-  // pairs of one step are visited row-major, close_contacts_calculator.py:104-124)
-  std::sort(out, out + have, [](const citam_pair& a, const citam_pair& b) {
-    if (a.first_step != b.first_step) return a.first_step < b.first_step;
-    if (a.a1 != b.a1) return a.a1 < b.a1;
-    return a.a2 < b.a2;
-  });
-  return CITAM_OK;
+  return rc;
 }
 
-int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, uint64_t* n) {
-  if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
+// Coordinate records ordered by (floor, sx, sy), into a DEVICE buffer.
+int citam_export_coords_device(citam_engine* e, citam_coord* out_device, uint64_t capacity, uint64_t* n) {
+  if (!e || !n || (capacity && !out_device)) return fail(CITAM_ERR_INVALID, "null argument");
   int rc = check_overflow(e);
   if (rc) return rc;
   uint64_t have = 0;
@@ -1982,32 +2310,81 @@ int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, ui
   *n = have;
   if (have == 0) return CITAM_OK;
   if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu coords, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
-  citam_coord* tmp = nullptr;
-  CK(cudaMalloc(&tmp, sizeof(citam_coord) * have));
-  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
   if (e->hist) {
-    Timed tm(e, CITAM_K_FINALIZE);
+    // ordered compaction: per-CTA counts of every floor, one scan, then the writes
+    std::vector<unsigned long long> first(e->F + 1, 0);
     for (int f = 0; f < e->F; ++f) {
-      const FloorDev& fd = e->floors_h[f];
-      long long nb = (long long)fd.hist_w * fd.hist_h;
-      if (nb == 0) continue;
-      k_hist_compact<<<(unsigned)((nb + 255) / 256), 256, 0, e->stream>>>(e->hist + fd.hist_base, nb, f, fd.hist_w,
-                                                                          2 * fd.minx, 2 * fd.miny, tmp, have, e->ctr_d);
+      long long nb = (long long)e->floors_h[f].hist_w * e->floors_h[f].hist_h;
+      first[f + 1] = first[f] + (unsigned long long)((nb + kHistThreads - 1) / kHistThreads);
     }
-  } else {
+    const unsigned long long nblk = first[e->F];
+    uint32_t *counts = nullptr, *scratch = nullptr;
+    CK(cudaMalloc(&counts, sizeof(uint32_t) * std::max<unsigned long long>(1, nblk)));
+    CK(cudaMalloc(&scratch, sizeof(uint32_t) * rsort::scan_scratch_elems(nblk)));
+    cudaError_t err = cudaSuccess;
+    {
+      Timed tm(e, CITAM_K_FINALIZE);
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int f = 0; f < e->F; ++f) {
+          const FloorDev& fd = e->floors_h[f];
+          long long nb = (long long)fd.hist_w * fd.hist_h;
+          if (nb == 0) continue;
+          k_hist_ordered<<<(unsigned)(first[f + 1] - first[f]), kHistThreads, 0, e->stream>>>(
+              e->hist + fd.hist_base, nb, fd.hist_w, fd.hist_h, f, 2 * fd.minx, 2 * fd.miny, counts + first[f],
+              pass ? out_device : nullptr, have);
+          e->launches++;
+        }
+        if (pass == 0) err = rsort::scan_u32(counts, nblk, scratch, e->stream);
+        if (err != cudaSuccess) break;
+      }
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(counts); cudaFree(scratch);
+    if (err != cudaSuccess) return fail(CITAM_ERR_CUDA, "coordinate export failed: %s", cudaGetErrorString(err));
+    return CITAM_OK;
+  }
+  CoordEntry *a = nullptr, *b = nullptr;
+  CK(cudaMalloc(&a, sizeof(CoordEntry) * have));
+  CK(cudaMalloc(&b, sizeof(CoordEntry) * have));
+  CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
+  {
     Timed tm(e, CITAM_K_FINALIZE);
-    k_compact_coords<<<(unsigned)((e->coord_cap + 255) / 256), 256, 0, e->stream>>>(e->coords, e->coord_cap, tmp, have, e->ctr_d);
+    k_compact_coord_entries<<<(unsigned)((e->coord_cap + 255) / 256), 256, 0, e->stream>>>(e->coords, e->coord_cap, a, have, e->ctr_d);
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, tmp, sizeof(citam_coord) * have, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  rsort::Pass passes[8];
+  int np = rsort::plan_word(passes, 0, 32);
+  np += rsort::plan_word(passes + np, 1, 32);
+  uint4* res = nullptr;
+  rc = device_sort(e, reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(b), have, passes, np, CoordKey(), &res);
+  if (rc == CITAM_OK) {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_coord_entries_to_records<<<(unsigned)((have + 255) / 256), 256, 0, e->stream>>>(reinterpret_cast<CoordEntry*>(res), have, out_device);
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(CITAM_ERR_CUDA, "coordinate export failed: %s", cudaGetErrorString(err));
+  }
+  cudaFree(a); cudaFree(b);
+  return rc;
+}
+
+int citam_export_coords(citam_engine* e, citam_coord* out, uint64_t capacity, uint64_t* n) {
+  if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
+  uint64_t have = 0;
+  int rc = citam_coord_count(e, &have);
+  if (rc) return rc;
+  *n = have;
+  if (have == 0) return check_overflow(e);
+  if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu coords, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
+  citam_coord* tmp = nullptr;
+  CK(cudaMalloc(&tmp, sizeof(citam_coord) * have));
+  rc = citam_export_coords_device(e, tmp, have, n);
+  if (rc == CITAM_OK) {
+    cudaError_t err = cudaMemcpyAsync(out, tmp, sizeof(citam_coord) * have, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(CITAM_ERR_CUDA, "coordinate export failed: %s", cudaGetErrorString(err));
+  }
   cudaFree(tmp);
-  std::sort(out, out + have, [](const citam_coord& a, const citam_coord& b) {
-    if (a.floor != b.floor) return a.floor < b.floor;
-    if (a.sx != b.sx) return a.sx < b.sx;
-    return a.sy < b.sy;
-  });
-  return CITAM_OK;
+  return rc;
 }
 
 int citam_export_agent_durations(citam_engine* e, uint64_t* out) {
@@ -2020,6 +2397,7 @@ int citam_export_agent_durations(citam_engine* e, uint64_t* out) {
   return CITAM_OK;
 }
 
+// The contact log in the order the reference visits contacts: (step, a1, a2), sorted on the device.
 int citam_export_contact_log(citam_engine* e, citam_contact* out, uint64_t capacity, uint64_t* n) {
   if (!e || !n || (capacity && !out)) return fail(CITAM_ERR_INVALID, "null argument");
   int rc = check_overflow(e);
@@ -2027,18 +2405,33 @@ int citam_export_contact_log(citam_engine* e, citam_contact* out, uint64_t capac
   citam_counters c;
   rc = citam_get_counters(e, &c);
   if (rc) return rc;
-  *n = c.log_records;
-  if (c.log_records == 0) return CITAM_OK;
-  if (capacity < c.log_records) return fail(CITAM_ERR_CAPACITY, "output holds %llu records, %llu needed", (unsigned long long)capacity, (unsigned long long)c.log_records);
-  CK(cudaMemcpyAsync(out, e->log, sizeof(citam_contact) * c.log_records, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  // deterministic order: (step, a1, a2) == the order the reference visits contacts
-  std::sort(out, out + c.log_records, [](const citam_contact& a, const citam_contact& b) {
-    if (a.step != b.step) return a.step < b.step;
-    if (a.a1 != b.a1) return a.a1 < b.a1;
-    return a.a2 < b.a2;
-  });
-  return CITAM_OK;
+  const uint64_t have = c.log_records;
+  *n = have;
+  if (have == 0) return CITAM_OK;
+  if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu records, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
+  uint4 *a = nullptr, *b = nullptr;
+  citam_contact* packed = nullptr;
+  CK(cudaMalloc(&a, sizeof(uint4) * have));
+  CK(cudaMalloc(&b, sizeof(uint4) * have));
+  CK(cudaMalloc(&packed, sizeof(citam_contact) * have));
+  CK(cudaMemcpyAsync(a, e->log, sizeof(uint4) * have, cudaMemcpyDeviceToDevice, e->stream));
+  rsort::Pass passes[12];
+  int np = 0;
+  const int ab = bits_of((unsigned long long)e->N - 1);
+  np += rsort::plan_word(passes + np, 0, ab);
+  np += rsort::plan_word(passes + np, 1, ab);
+  np += rsort::plan_word(passes + np, 2, std::min(24, bits_of(e->max_step)));
+  uint4* res = nullptr;
+  rc = device_sort(e, a, b, have, passes, np, LogKey(), &res);
+  if (rc == CITAM_OK) {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_log_to_contacts<<<(unsigned)((have + 255) / 256), 256, 0, e->stream>>>(res, have, packed);
+    cudaError_t err = cudaMemcpyAsync(out, packed, sizeof(citam_contact) * have, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = fail(CITAM_ERR_CUDA, "contact log export failed: %s", cudaGetErrorString(err));
+  }
+  cudaFree(a); cudaFree(b); cudaFree(packed);
+  return rc;
 }
 
 int citam_clear_contact_log(citam_engine* e) {
@@ -2048,8 +2441,10 @@ int citam_clear_contact_log(citam_engine* e) {
   return CITAM_OK;
 }
 
-int citam_statistics(citam_engine* e, citam_stats* out) {
-  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+// Statistics in two halves, so that ranks holding disjoint parts of one run's pair table can
+// all-reduce the per-agent arrays in between (citam_stats_arrays_device).
+int citam_statistics_begin(citam_engine* e) {
+  if (!e) return fail(CITAM_ERR_INVALID, "null engine");
   int rc = check_overflow(e);
   if (rc) return rc;
   size_t n = (size_t)e->N;
@@ -2059,6 +2454,25 @@ int citam_statistics(citam_engine* e, citam_stats* out) {
   {
     Timed tm(e, CITAM_K_FINALIZE);
     k_stats_pairs<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, e->agent_nev, e->agent_has, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return CITAM_OK;
+}
+
+int citam_stats_arrays_device(citam_engine* e, void** events_per_agent, void** has_contact, uint64_t* n_elements) {
+  if (!e || !events_per_agent || !has_contact || !n_elements) return fail(CITAM_ERR_INVALID, "null argument");
+  *events_per_agent = e->agent_nev;
+  *has_contact = e->agent_has;
+  *n_elements = (uint64_t)e->N;
+  return CITAM_OK;
+}
+
+int citam_statistics_end(citam_engine* e, citam_stats* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
     k_stats_agents<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->agent_nev, e->agent_has, e->N, e->ctr_d);
   }
   CK(cudaGetLastError());
@@ -2072,6 +2486,13 @@ int citam_statistics(citam_engine* e, citam_stats* out) {
   out->max_events_per_agent = c.stats[4];
   out->reserved = 0;
   return CITAM_OK;
+}
+
+int citam_statistics(citam_engine* e, citam_stats* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = citam_statistics_begin(e);
+  if (rc) return rc;
+  return citam_statistics_end(e, out);
 }
 
 int citam_get_timings(citam_engine* e, citam_timings* out) {
@@ -2091,24 +2512,100 @@ int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elemen
   return CITAM_OK;
 }
 
+int citam_hist_device(citam_engine* e, void** ptr, uint64_t* n_elements) {
+  if (!e || !ptr || !n_elements) return fail(CITAM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_ready(e, 1);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  *ptr = e->hist;
+  *n_elements = (uint64_t)e->hist_total;
+  return CITAM_OK;
+}
+
+// The table's records grouped by destination, hash(a1, a2) mod n_parts, into a DEVICE buffer:
+// part k occupies out[sum(counts[0..k)) .. + counts[k]).  The send side of the all-to-all.
+int citam_partition_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t capacity, int32_t n_parts, uint64_t* counts) {
+  if (!e || !counts || (capacity && !out_device)) return fail(CITAM_ERR_INVALID, "null argument");
+  if (n_parts < 1 || n_parts > kMaxParts) return fail(CITAM_ERR_INVALID, "n_parts must be in 1..%d", kMaxParts);
+  CK(cudaSetDevice(e->device));
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  unsigned long long* cnt_d = nullptr;
+  CK(cudaMalloc(&cnt_d, sizeof(unsigned long long) * kMaxParts));
+  CK(cudaMemsetAsync(cnt_d, 0, sizeof(unsigned long long) * kMaxParts, e->stream));
+  const unsigned blocks = (unsigned)std::min<unsigned long long>(148 * 16, (e->pair_cap + 255) / 256);
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_partition_count<<<blocks, 256, 0, e->stream>>>(e->pairs, e->pair_cap, (uint32_t)n_parts, cnt_d);
+  }
+  unsigned long long h[kMaxParts], cur[kMaxParts];
+  CK(cudaMemcpyAsync(h, cnt_d, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  unsigned long long tot = 0;
+  for (int k = 0; k < n_parts; ++k) { counts[k] = h[k]; cur[k] = tot; tot += h[k]; }
+  for (int k = n_parts; k < kMaxParts; ++k) cur[k] = tot;
+  if (tot > capacity) {
+    cudaFree(cnt_d);
+    return fail(CITAM_ERR_CAPACITY, "output holds %llu pairs, %llu needed", (unsigned long long)capacity, tot);
+  }
+  if (tot) {
+    CK(cudaMemcpyAsync(cnt_d, cur, sizeof cur, cudaMemcpyHostToDevice, e->stream));
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_partition_scatter<<<blocks, 256, 0, e->stream>>>(e->pairs, e->pair_cap, (uint32_t)n_parts, cnt_d, out_device, capacity);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(cnt_d);
+  return CITAM_OK;
+}
+
+// Merge pair records exported by another engine (DEVICE buffer): steps and events add, the first
+// contact step is the minimum.  Only the pair table is touched (see the header).
+int citam_merge_pairs_device(citam_engine* e, const citam_pair* pairs_device, uint64_t n) {
+  if (!e || (n && !pairs_device)) return fail(CITAM_ERR_INVALID, "null argument");
+  if (!n) return CITAM_OK;
+  CK(cudaSetDevice(e->device));
+  int rc = join_side_stream(e);
+  if (rc) return rc;
+  if (e->pair_auto) {  // room for every record before the first one is applied
+    citam_counters c;
+    rc = citam_get_counters(e, &c);
+    if (rc) return rc;
+    unsigned long long ncap = e->pair_cap;
+    while ((c.pair_slots_used + n) * 2 > ncap) ncap *= 2;
+    if (ncap != e->pair_cap) {
+      rc = rehash_pairs(e, ncap);
+      if (rc == CITAM_ERR_CAPACITY) return fail(CITAM_ERR_CAPACITY, "out of device memory growing the pair table to %llu slots", ncap);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaMemsetAsync(e->flag_d, 0, sizeof(int), e->stream));
+  Params p = make_params(e);
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_merge_pairs<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, pairs_device, n, e->flag_d);
+  }
+  CK(cudaGetLastError());
+  int bad = 0;
+  rc = read_flag(e, &bad);
+  if (rc) return rc;
+  if (bad) return fail(CITAM_ERR_INVALID, "a merged pair record is malformed (need a1 < a2 < n_agents, duration < 2^24, events < 2^16)");
+  e->max_step = 0xFFFFFFu;  // merged first-contact steps are not bounded by what this engine ran
+  return check_overflow(e);
+}
+
 int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n) {
   if (!e || (n && !pairs)) return fail(CITAM_ERR_INVALID, "null argument");
   if (!n) return CITAM_OK;
   CK(cudaSetDevice(e->device));
-  for (uint64_t i = 0; i < n; ++i)
-    if (pairs[i].a1 >= pairs[i].a2 || pairs[i].a2 >= (uint32_t)e->N) return fail(CITAM_ERR_INVALID, "bad pair record %llu", (unsigned long long)i);
   citam_pair* tmp = nullptr;
   CK(cudaMalloc(&tmp, sizeof(citam_pair) * n));
-  CK(cudaMemcpyAsync(tmp, pairs, sizeof(citam_pair) * n, cudaMemcpyHostToDevice, e->stream));
-  Params p = make_params(e);
-  {
-    Timed tm(e, CITAM_K_FINALIZE);
-    k_merge_pairs<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, tmp, n);
-  }
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(e->stream));
+  cudaError_t err = cudaMemcpyAsync(tmp, pairs, sizeof(citam_pair) * n, cudaMemcpyHostToDevice, e->stream);
+  int rc = err == cudaSuccess ? citam_merge_pairs_device(e, tmp, n) : fail(CITAM_ERR_CUDA, "copy failed: %s", cudaGetErrorString(err));
+  cudaStreamSynchronize(e->stream);
   cudaFree(tmp);
-  return check_overflow(e);
+  return rc;
 }
 
 int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n) {
@@ -2121,7 +2618,7 @@ int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n) {
     const citam_coord& c = coords[i];
     if (c.floor < 0 || c.floor >= e->F) return fail(CITAM_ERR_INVALID, "bad coordinate record %llu", (unsigned long long)i);
     const FloorDev& fd = e->floors_h[c.floor];
-    if (e->hist && (c.sx < 2 * fd.minx || c.sx - 2 * fd.minx >= fd.hist_w || c.sy < 2 * fd.miny || c.sy - 2 * fd.miny >= fd.hist_h))
+    if (c.sx < 2 * fd.minx || c.sx - 2 * fd.minx >= std::max(1, 2 * fd.W - 1) || c.sy < 2 * fd.miny || c.sy - 2 * fd.miny >= std::max(1, 2 * fd.H - 1))
       return fail(CITAM_ERR_INVALID, "coordinate record %llu lies outside floor %d", (unsigned long long)i, c.floor);
   }
   citam_coord* tmp = nullptr;

@@ -1,19 +1,26 @@
-"""Multi-GPU: time-block sharding of one scenario (or replica sharding) + the final reduction.
+"""Multi-GPU: one scenario sharded by time over the ranks (or replica sharding) + the final exchange.
 
 The step loop needs no per-step communication: every accumulator is commutative,
-so rank r runs time blocks r, r+G, r+2G, ... of the day for ALL agents (each block re-evaluates
-the predicate one step before its first step) and the ranks meet once, at the end:
+so rank r runs its own part of the day for ALL agents -- a contiguous range of steps (the default:
+contact runs then aggregate over the whole range) or round-robin time blocks -- each part
+re-evaluating the predicate one step before its first step, and the ranks meet once, at the end,
+on DEVICE buffers (NCCL over NVLink through torch.distributed):
 
-  per-agent contact seconds   all-reduce (sum)
-  pair records                all-gather, merged (steps +, events +, first step min)
-  coordinate records          all-gather, merged (count +)
+  per-agent contact seconds   all-reduce (sum) of the engine's counter array
+  coordinate histogram        all-reduce (sum) of the dense histogram
+  pair records                all-to-all by hash(a1, a2) mod G of the partitioned table
+                              (citam_partition_pairs_device), then a device merge
+                              (citam_merge_pairs_device: steps +, events +, first step min):
+                              every rank ends with the complete records of its share of the pairs
+  statistics                  per-share integer sums; the per-agent event counts are all-reduced
 
-`torch.distributed` is the plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests); the merge
-itself is plain integer work on the host or, through `citam_merge_pairs/coords`, on the device.
+This is the parallel runner over "timestep blocks" that the reference's `run_serial` docstring
+asks for (citam/engine/core/simulation.py:222-227).  The host-side merges below do the same on
+numpy records (gloo CPU tests, small runs that want the whole table on every rank).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -117,29 +124,144 @@ def reduce_tables(pairs: np.ndarray, coords: np.ndarray, durations: np.ndarray):
     )
 
 
-class ShardedRun:
-    """One scenario over the ranks of the current process group, sharded by time blocks."""
+def plan_range(total_timesteps: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous share [t0, t1) of rank `rank`; the shares tile [0, T) exactly."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad range plan arguments")
+    return (total_timesteps * rank) // world, (total_timesteps * (rank + 1)) // world
 
-    def __init__(self, engine, total_timesteps: int, block: int = 1024):
+
+_M1, _M2 = np.uint64(0xFF51AFD7ED558CCD), np.uint64(0xC4CEB9FE1A85EC53)
+
+
+def part_of(a1: np.ndarray, a2: np.ndarray, n_parts: int) -> np.ndarray:
+    """Destination rank of a pair: the device's `part_of` (mix64(a1 << 32 | a2) >> 40) mod n_parts."""
+    k = (np.asarray(a1, np.uint64) << np.uint64(32)) | np.asarray(a2, np.uint64)
+    with np.errstate(over="ignore"):
+        k = k ^ (k >> np.uint64(33))
+        k = k * _M1
+        k = k ^ (k >> np.uint64(33))
+        k = k * _M2
+        k = k ^ (k >> np.uint64(33))
+    return ((k >> np.uint64(40)) % np.uint64(n_parts)).astype(np.int64)
+
+
+def exchange_pairs_host(pairs: np.ndarray) -> np.ndarray:
+    """Host mirror of the device exchange (gloo has no all-to-all): every rank ends with the merged
+    records of its share of the pairs."""
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    parts = all_gather_records(np.ascontiguousarray(pairs, PAIR))
+    mine = [p[part_of(p["a1"], p["a2"], world) == rank] for p in parts]
+    return merge_pair_records(mine)
+
+
+class _DevView:
+    """A torch tensor over engine-owned device memory (no copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def device_tensor(ptr: int, n: int, typestr: str = "<i8"):
+    import torch
+
+    return torch.as_tensor(_DevView(ptr, n, typestr), device="cuda")
+
+
+class ShardedRun:
+    """One scenario over the ranks of the current process group, sharded by time.
+
+    `block=None`: rank r runs the contiguous range `plan_range(T, G, r)` in one `citam_run` (contact
+    runs aggregate over the whole range); `block=k`: round-robin blocks of k steps (`plan_blocks`)."""
+
+    def __init__(self, engine, total_timesteps: int, block: Optional[int] = None):
         dist = _dist()
         self.engine = engine
         self.T = int(total_timesteps)
-        self.block = int(block)
+        self.block = None if block is None else int(block)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.info: Dict[str, float] = {}
+
+    def plan(self) -> List[Tuple[int, int]]:
+        if self.block is None:
+            return [plan_range(self.T, self.world, self.rank)]
+        return plan_blocks(self.T, self.block, self.world, self.rank)
 
     def run(self):
-        for t0, t1 in plan_blocks(self.T, self.block, self.world, self.rank):
-            self.engine.run(t0, t1)
+        for t0, t1 in self.plan():
+            if t1 > t0:
+                self.engine.run(t0, t1)
         return self
 
-    def reduce(self, into_engine: bool = False):
-        """All ranks get the merged tables; with `into_engine` the other ranks' records are also
-        merged into this rank's device tables (`citam_merge_pairs/coords`)."""
-        pairs, coords = self.engine.pairs(), self.engine.coords()
-        gp, gc = all_gather_records(pairs), all_gather_records(coords)
-        if into_engine:
-            for r in range(self.world):
+    # -- the final exchange on device buffers (NCCL) --------------------------------------------
+    def reduce(self):
+        """After this every rank's engine holds: the whole run's per-agent contact seconds and
+        coordinate histogram, and the complete pair records of its share of the pairs
+        (hash(a1, a2) mod G == rank).  Returns the whole run's statistics sums."""
+        import torch
+
+        dist = _dist()
+        eng, G = self.engine, self.world
+        ptr, n = eng.agent_durations_device()
+        dist.all_reduce(device_tensor(ptr, n))
+        hptr, hn = eng.hist_device()
+        if hn:
+            dist.all_reduce(device_tensor(hptr, hn))
+        elif G > 1:
+            # hashed histogram (huge lattices): records through the host
+            gc = all_gather_records(eng.coords())
+            for r in range(G):
                 if r != self.rank:
-                    self.engine.merge(gp[r], gc[r])
-            return self.engine.pairs(), self.engine.coords(), self.engine.agent_durations().astype(np.int64)
-        return merge_pair_records(gp), merge_coord_records(gc), all_reduce_sum(self.engine.agent_durations())
+                    eng.merge(np.zeros(0, PAIR), gc[r])
+        # pair table: partition -> all-to-all -> merge
+        n_local = eng.pair_count()
+        send = torch.empty((max(1, n_local), 3), dtype=torch.int64, device="cuda")
+        counts = eng.partition_pairs_device(send.data_ptr(), n_local, G)
+        send_counts = torch.from_numpy(counts.astype(np.int64)).cuda()
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        in_split = counts.astype(np.int64).tolist()
+        out_split = recv_counts.cpu().tolist()
+        n_recv = int(sum(out_split))
+        recv = torch.empty((max(1, n_recv), 3), dtype=torch.int64, device="cuda")
+        dist.all_to_all_single(recv[:n_recv], send[:n_local], out_split, in_split)
+        torch.cuda.synchronize()
+        eng.clear_pairs()
+        eng.merge_pairs_device(recv.data_ptr(), n_recv)
+        del send, recv
+        self.info = {
+            "pairs_local_before": int(n_local), "pairs_received": n_recv, "pairs_after": eng.pair_count(),
+            "a2a_bytes_sent": int(24 * (n_local - int(counts[self.rank]))),
+            "allreduce_bytes": int(8 * n + 8 * hn),
+        }
+        return self.statistics()
+
+    def statistics(self) -> Dict[str, int]:
+        """The run's statistics sums from the rank-partitioned pair table."""
+        import torch
+
+        dist = _dist()
+        eng = self.engine
+        eng.statistics_begin()
+        a, b, n = eng.stats_arrays_device()
+        dist.all_reduce(device_tensor(a, n, "<i4"))
+        dist.all_reduce(device_tensor(b, n, "<i4"))
+        torch.cuda.synchronize()
+        s = eng.statistics_end()
+        t = torch.tensor([s["total_duration"], s["n_pairs"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        s["total_duration"], s["n_pairs"] = int(t[0].item()), int(t[1].item())
+        return s
+
+    # -- small runs: the whole tables on every rank, through the host --------------------------------
+    def gather_tables(self):
+        """(pairs, coords, durations) of the whole run on every rank, merged on the host from the
+        ranks' tables.  Call instead of -- or after -- `reduce` (after it the per-rank tables are
+        disjoint shares and the counters / histogram are already global)."""
+        reduced = bool(self.info)
+        pairs = merge_pair_records(all_gather_records(self.engine.pairs()))
+        if reduced:
+            return pairs, self.engine.coords(), self.engine.agent_durations().astype(np.int64)
+        return (pairs, merge_coord_records(all_gather_records(self.engine.coords())),
+                all_reduce_sum(self.engine.agent_durations()))

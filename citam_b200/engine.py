@@ -211,17 +211,72 @@ class DeviceEngine:
         }
 
     def merge(self, pairs: np.ndarray, coords: np.ndarray) -> None:
+        """Other ranks' records into this engine's tables (pair table and histogram only: the
+        per-agent contact seconds are reduced separately)."""
         pairs = np.ascontiguousarray(pairs, L.PAIR)
         coords = np.ascontiguousarray(coords, L.COORD)
         L.check(self.lib.citam_merge_pairs(self._h, L.ptr(pairs), len(pairs)))
         L.check(self.lib.citam_merge_coords(self._h, L.ptr(coords), len(coords)))
 
+    # -- device-resident results (multi-GPU exchange, large runs) ------------------------------
     def agent_durations_device(self):
-        """(device pointer, n) of the uint32 per-agent counters, for NCCL all-reduce."""
+        """(device pointer, n) of the live uint64 per-agent contact seconds, for the NCCL all-reduce."""
         p = C.c_void_p()
         n = C.c_uint64()
         L.check(self.lib.citam_agent_durations_device(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def hist_device(self):
+        """(device pointer, n) of the dense uint64 coordinate histogram; (None, 0) when hashed."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        L.check(self.lib.citam_hist_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stats_arrays_device(self):
+        """(events-per-agent pointer, has-contact pointer, n): uint32 arrays filled by statistics_begin."""
+        a, b = C.c_void_p(), C.c_void_p()
+        n = C.c_uint64()
+        L.check(self.lib.citam_stats_arrays_device(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def pair_count(self) -> int:
+        n = C.c_uint64()
+        L.check(self.lib.citam_pair_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def export_pairs_device(self, dev_ptr: int, capacity: int) -> int:
+        """Pair records in first-contact order into a caller-owned DEVICE buffer; returns the count."""
+        n = C.c_uint64()
+        L.check(self.lib.citam_export_pairs_device(self._h, C.c_void_p(dev_ptr), int(capacity), C.byref(n)))
+        return int(n.value)
+
+    def export_coords_device(self, dev_ptr: int, capacity: int) -> int:
+        n = C.c_uint64()
+        L.check(self.lib.citam_export_coords_device(self._h, C.c_void_p(dev_ptr), int(capacity), C.byref(n)))
+        return int(n.value)
+
+    def partition_pairs_device(self, dev_ptr: int, capacity: int, n_parts: int) -> np.ndarray:
+        """All pair records grouped by hash(a1, a2) mod n_parts into a DEVICE buffer; returns the
+        per-part counts (uint64[n_parts])."""
+        counts = np.zeros(n_parts, np.uint64)
+        L.check(self.lib.citam_partition_pairs_device(self._h, C.c_void_p(dev_ptr), int(capacity), int(n_parts),
+                                                      counts.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return counts
+
+    def clear_pairs(self) -> None:
+        L.check(self.lib.citam_clear_pairs(self._h))
+
+    def merge_pairs_device(self, dev_ptr: int, n: int) -> None:
+        L.check(self.lib.citam_merge_pairs_device(self._h, C.c_void_p(dev_ptr), int(n)))
+
+    def statistics_begin(self) -> None:
+        L.check(self.lib.citam_statistics_begin(self._h))
+
+    def statistics_end(self) -> Dict[str, int]:
+        s = L.Stats()
+        L.check(self.lib.citam_statistics_end(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in L.Stats._fields_ if k != "reserved"}
 
 
 def statistics_from_sums(s: Dict[str, int]):

@@ -20,11 +20,15 @@
  * usable.
  *
  * Limits (checked; violations return CITAM_ERR_INVALID or CITAM_ERR_CAPACITY):
- *   floors <= 63, spaces per floor <= 32767, steps < 2^24, |coordinates| < 2^26,
- *   per-step stride of a segment within int16, contact-steps per pair < 2^24 and
- *   events per pair < 2^16, steps_per_chunk <= 256.  Itinerary coordinates are
- *   integers (the reference's navigation lattice); contact positions are their
- *   midpoints, reported as (x1+x2, y1+y2).
+ *   floors <= 63, spaces per floor <= 32767, location-table sides <= 65536,
+ *   steps < 2^24 - 1, |coordinates| < 2^26, per-step stride of a segment within
+ *   int16, contact-steps per pair < 2^24 and events per pair < 2^16,
+ *   steps_per_chunk <= 1024, fewer than 2^32 records per export.  Itinerary
+ *   coordinates are integers (the reference's navigation lattice); contact
+ *   positions are their midpoints, reported as (x1+x2, y1+y2).
+ *   citam_load_itineraries checks the segment store on the device: seg_off
+ *   non-decreasing inside [0, n_segs], t0 strictly increasing per agent, floors
+ *   0..62, a zero-velocity last segment per agent.
  */
 #ifndef CITAM_B200_H
 #define CITAM_B200_H
@@ -35,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CITAM_ABI_VERSION 1
+#define CITAM_ABI_VERSION 2
 
 typedef enum {
   CITAM_OK = 0,
@@ -148,7 +152,8 @@ typedef struct {
   uint64_t kernel_launches;
   uint64_t pair_slots_used, coord_slots_used, log_records;
   uint64_t overflow;      /* bit0 pair table, bit1 coord table, bit2 log          */
-  uint64_t contact_runs;  /* table updates: a run of contact-steps of a stationary pair is one */
+  uint64_t contact_runs;  /* table updates: a run of contact-steps of a stationary pair is one,
+                             however many chunks of the citam_run range it crosses        */
 } citam_counters;
 
 #define CITAM_N_KERNELS 8
@@ -209,6 +214,11 @@ int citam_states_range(citam_engine* e, int32_t t_begin, int32_t t_end, citam_ag
 int citam_reset(citam_engine* e); /* clear all accumulators, keep facility + itineraries */
 
 /* ---- results: replaces ContactEvents / extract_* ------------------------ */
+/* Rows come in the reference's own order, produced by a device radix sort (K5):
+ * pairs by (first contact step, a1, a2) = dict insertion order of
+ * ContactEvents.contact_data (contacts.py:135-183), coordinates by (floor, sx, sy),
+ * the contact log by (step, a1, a2) = the visiting order of
+ * close_contacts_calculator.py:104-124. */
 int citam_pair_count(citam_engine* e, uint64_t* n);
 int citam_export_pairs(citam_engine* e, citam_pair* out, uint64_t capacity, uint64_t* n);
 int citam_export_agent_durations(citam_engine* e, uint64_t* out /* [n_agents] */);
@@ -220,13 +230,45 @@ int citam_statistics(citam_engine* e, citam_stats* out);
 int citam_get_counters(citam_engine* e, citam_counters* out);
 int citam_get_timings(citam_engine* e, citam_timings* out);
 
-/* Device views for the multi-GPU reduction (torch.distributed/NCCL all-reduce
- * on engine memory): per-agent contact seconds, uint64 [n_agents].  The pointer is the live
- * counter array: reduce into a copy if the engine goes on accumulating or merging. */
+/* ---- multi-GPU: one scenario sharded by time ranges over G engines -------- */
+/* (the "timestep blocks" parallel runner the reference's docstring asks for,
+ *  simulation.py:222-227).  Every accumulator is commutative, so the ranks meet
+ *  once, at the end; the collectives themselves (NCCL through torch.distributed)
+ *  run on the DEVICE buffers these calls expose or fill:
+ *    per-agent contact seconds   all-reduce(sum) on citam_agent_durations_device
+ *    dense coordinate histogram  all-reduce(sum) on citam_hist_device
+ *    pair table                  citam_partition_pairs_device -> all-to-all by
+ *                                hash(a1,a2) mod G -> citam_clear_pairs +
+ *                                citam_merge_pairs_device: every rank ends with
+ *                                the complete records of its share of the pairs
+ *    statistics                  citam_statistics_begin, all-reduce(sum) on the two
+ *                                citam_stats_arrays_device arrays, citam_statistics_end
+ *                                (total_duration and n_pairs are then per-share sums:
+ *                                add them over the ranks)
+ * Device views are the live arrays: uint64 [n_agents] contact seconds, uint64
+ * [n] histogram buckets (NULL/0 when the hashed histogram is in use), uint32
+ * [n_agents] events per agent and has-contact flags. */
 int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements);
-/* Merge pair / coordinate records exported by another engine (other rank). */
+int citam_hist_device(citam_engine* e, void** ptr, uint64_t* n_elements);
+int citam_export_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t capacity, uint64_t* n);
+int citam_export_coords_device(citam_engine* e, citam_coord* out_device, uint64_t capacity, uint64_t* n);
+/* All pairs of the table grouped by destination = hash(a1,a2) mod n_parts (n_parts <= 64):
+ * part k is out_device[sum(counts[0..k)) ... + counts[k]); counts is a HOST array. */
+int citam_partition_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t capacity,
+                                 int32_t n_parts, uint64_t* counts);
+int citam_clear_pairs(citam_engine* e); /* empty the pair table only */
+/* Merge pair / coordinate records exported by another engine (other rank):
+ * steps and events add, first contact step = min.  Only the pair table /
+ * histogram are touched -- per-agent contact seconds are NOT updated (reduce
+ * them with the all-reduce above).  A library-sized pair table is grown before
+ * the first record is applied. */
+int citam_merge_pairs_device(citam_engine* e, const citam_pair* pairs_device, uint64_t n);
 int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n);
 int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n);
+int citam_statistics_begin(citam_engine* e);
+int citam_stats_arrays_device(citam_engine* e, void** events_per_agent, void** has_contact,
+                              uint64_t* n_elements);
+int citam_statistics_end(citam_engine* e, citam_stats* out);
 
 #ifdef __cplusplus
 }

@@ -153,3 +153,109 @@ def test_capacity_errors_are_reported_not_silent():
     eng.run(0, T)
     assert len(eng.pairs()) == K * (K - 1) // 2
     eng.close()
+
+
+def test_one_table_update_per_contact_run_whatever_the_chunking():
+    """A stationary pair's contact run is ONE table update per citam_run range: the number of
+    updates does not depend on how many chunks the range is cut into, and the results do not either."""
+    from citam_b200.engine import DeviceEngine
+
+    fac = _fac()
+    T = 900
+    itins = []
+    for a in range(12):  # six pairs sitting side by side in an office for most of the run, a few walkers
+        x, y = 40 + 3 * (a // 2), 80 + 2 * (a % 2)
+        itins.append([(None, None)] * (5 + a) + [((x, y), 0)] * (T - 20 - 2 * a) + [(None, None)])
+    for a in range(4):
+        itins.append([((30 + (t % 40), 82), 0) for t in range(T)])
+    runs, tabs = [], []
+    for chunk in (7, 64, 0):
+        eng = DeviceEngine(len(itins), 1, 6.0, steps_per_chunk=chunk)
+        eng.load_geometry(fac.geometry)
+        eng.load_itineraries(itins)
+        eng.run(0, T)
+        runs.append(eng.counters()["contact_runs"])
+        tabs.append(tables_of(eng))
+        eng.close()
+    assert runs[0] == runs[1] == runs[2], runs
+    assert tabs[0] == tabs[1] == tabs[2]
+    sim = run_port(itins, fac.geometry, 6.0, T)
+    want = tables_of_port(sim, 1)
+    assert tabs[0] == (want[0], want[1], want[2])
+    # far fewer updates than contact-steps
+    assert runs[0] * 5 < sum(r[4] for r in want[0])
+
+
+def test_load_itineraries_rejects_stores_outside_the_documented_limits():
+    """include/citam_b200.h: the limits are checked on the device copy (CITAM_ERR_INVALID)."""
+    from citam_b200 import _lib as L
+    from citam_b200.engine import DeviceEngine
+
+    fac = _fac()
+    eng = DeviceEngine(3, 1, 6.0)
+    eng.load_geometry(fac.geometry)
+
+    def store(rows, off):
+        s = np.zeros(len(rows), L.SEGMENT)
+        for i, r in enumerate(rows):
+            s[i] = r + (0,)
+        return np.array(off, np.int64), s
+
+    good = [(0, 30, 100, 0, 0, 0), (5, 30, 100, 1, 0, 0), (9, 34, 100, 0, 0, 0), (0, 50, 100, 0, 0, 0), (2, 60, 100, 0, 0, 0)]
+    eng.load_segments(*store(good, [0, 3, 4, 5]))
+    eng.run(0, 20)
+    bad_cases = {
+        "seg_off decreases": (good, [0, 4, 3, 5]),
+        "t0 not increasing": ([(0, 30, 100, 0, 0, 0), (5, 30, 100, 1, 0, 0), (5, 34, 100, 0, 0, 0)] + good[3:], [0, 3, 4, 5]),
+        "negative t0": ([(-1, 30, 100, 0, 0, 0)] + good[1:], [0, 3, 4, 5]),
+        "t0 beyond 2^24": ([(0, 30, 100, 0, 0, 0), (5, 30, 100, 1, 0, 0), (1 << 24, 34, 100, 0, 0, 0)] + good[3:], [0, 3, 4, 5]),
+        "floor 63": (good[:4] + [(2, 60, 100, 0, 0, 63)], [0, 3, 4, 5]),
+        "negative floor": (good[:4] + [(2, 60, 100, 0, 0, -1)], [0, 3, 4, 5]),
+        "moving last segment": (good[:2] + [(9, 34, 100, 0, 2, 0)] + good[3:], [0, 3, 4, 5]),
+        "coordinate beyond 2^26": (good[:4] + [(2, 1 << 26, 100, 0, 0, 0)], [0, 3, 4, 5]),
+    }
+    for name, (rows, off) in bad_cases.items():
+        with pytest.raises(ValueError):
+            eng.load_segments(*store(rows, off))
+        with pytest.raises(L.CitamDeviceError):
+            eng.run(0, 5)  # a rejected store leaves the engine without itineraries
+    eng.load_segments(*store(good, [0, 3, 4, 5]))
+    with pytest.raises(ValueError):
+        eng.run(0, 1 << 24)  # steps < 2^24 - 1
+    eng.run(20, 30)
+    eng.close()
+
+
+def test_merge_grows_a_library_sized_table_and_rejects_malformed_records():
+    from citam_b200 import _lib as L
+    from citam_b200.engine import DeviceEngine
+
+    fac = _fac()
+    N = 6000
+    eng = DeviceEngine(N, 1, 6.0)
+    eng.load_geometry(fac.geometry)
+    rng = np.random.default_rng(3)
+    n = 5_000_000  # more than the library-sized table (2^22 slots) holds
+    a1 = rng.integers(0, N - 1, n).astype(np.uint32)
+    a2 = (a1 + 1 + rng.integers(0, N - 1 - a1)).astype(np.uint32)
+    rec = np.zeros(n, L.PAIR)
+    rec["a1"], rec["a2"], rec["first_step"], rec["n_events"], rec["duration"] = a1, a2, rng.integers(0, 1000, n), 1, 2
+    eng.merge(rec, np.zeros(0, L.COORD))
+    key = a1.astype(np.uint64) << np.uint64(32) | a2
+    uk, first_idx, cnt = np.unique(key, return_index=True, return_counts=True)
+    p = eng.pairs()
+    assert len(p) == len(uk)
+    assert int(p["duration"].sum()) == 2 * n and int(p["n_events"].sum()) == n
+    got_key = p["a1"].astype(np.uint64) << np.uint64(32) | p["a2"]
+    o = np.argsort(got_key)
+    assert (got_key[o] == uk).all() and (p["duration"][o] == 2 * cnt).all()
+    fmin = np.full(len(uk), 1 << 30)
+    np.minimum.at(fmin, np.searchsorted(uk, key), rec["first_step"])
+    assert (p["first_step"][o] == fmin).all()
+    assert (np.lexsort((p["a2"], p["a1"], p["first_step"])) == np.arange(len(p))).all()  # device sort order
+    assert eng.agent_durations().sum() == 0  # merging does not touch the per-agent counters
+    bad = rec[:4].copy()
+    bad["a2"][2] = bad["a1"][2]
+    with pytest.raises(ValueError):
+        eng.merge(bad, np.zeros(0, L.COORD))
+    eng.close()

@@ -75,14 +75,17 @@ def test_time_blocks_in_any_order_and_merge(synth):
     cuts = list(range(0, T, 500)) + [T]
     for i, (t0, t1) in enumerate(zip(cuts[:-1], cuts[1:])):
         (a if i % 2 == 0 else b).run(t0, t1)
-    a.merge(b.pairs(), b.coords())
-    assert tables_of(a) == want
+    dur_b = b.agent_durations()
+    a.merge(b.pairs(), b.coords())  # pair table + histogram; per-agent seconds are reduced separately
+    got = tables_of(a)
+    assert got[0] == want[0] and got[1] == want[1]
+    assert [int(x) + int(y) for x, y in zip(got[2], dur_b)] == want[2]
     a.close()
     b.close()
 
 
 def test_auto_capacity_grows(synth):
-    """Library-chosen pair capacity starts small and doubles when half full."""
+    """Library-chosen pair capacity starts small and is doubled while more than a quarter full."""
     fac, seg_off, segs, p, T, want, _ = synth
     eng = _engine(fac, seg_off, segs, p, steps_per_chunk=100)
     eng.run(0, T)
@@ -139,3 +142,48 @@ def test_replica_sweep_matches_oracle_per_replica():
         want = {d["name"]: d["value"] for d in port.statistics_from_pairs(rows)}
         assert r["statistics"] == want, spec
         assert r["contact_steps"] == g.contact_steps
+
+
+def test_partition_clear_merge_round_trip_on_device(synth):
+    """The multi-GPU exchange on one GPU: partition the pair table by hash(a1, a2) mod G into a
+    device buffer, empty the table, merge the parts back from device memory -> the same table; the
+    parts are where the host mirror of the hash says, and the device exports equal the host ones."""
+    import torch
+
+    from citam_b200 import _lib as L
+    from citam_b200 import distributed as D
+
+    fac, seg_off, segs, p, T, want, _ = synth
+    eng = _engine(fac, seg_off, segs, p)
+    eng.run(0, T)
+    n = eng.pair_count()
+    assert n == len(want[0])
+    for G in (1, 3, 8):
+        buf = torch.zeros((max(1, n), 3), dtype=torch.int64, device="cuda")
+        counts = eng.partition_pairs_device(buf.data_ptr(), n, G)
+        assert int(counts.sum()) == n
+        rec = buf.cpu().numpy().view(L.PAIR).reshape(-1)[:n]
+        part = D.part_of(rec["a1"], rec["a2"], G)
+        assert (part == np.repeat(np.arange(G), counts.astype(np.int64))).all()
+        eng.clear_pairs()
+        assert eng.pair_count() == 0
+        off = 0
+        for k in range(G):  # one merge per "sending rank"
+            eng.merge_pairs_device(buf.data_ptr() + 24 * off, int(counts[k]))
+            off += int(counts[k])
+        assert tables_of(eng) == want
+    # device-resident exports (sorted on the device) equal the host exports
+    out = torch.zeros((max(1, n), 3), dtype=torch.int64, device="cuda")
+    assert eng.export_pairs_device(out.data_ptr(), n) == n
+    assert out.cpu().numpy().view(L.PAIR).reshape(-1)[:n].tolist() == eng.pairs().tolist()
+    co = eng.coords()
+    outc = torch.zeros((max(1, len(co)), 3), dtype=torch.int64, device="cuda")
+    assert eng.export_coords_device(outc.data_ptr(), len(co)) == len(co)
+    assert outc.cpu().numpy().view(L.COORD).reshape(-1)[: len(co)].tolist() == co.tolist()
+    # statistics in two halves == in one call
+    s1 = eng.statistics_sums()
+    eng.statistics_begin()
+    assert eng.statistics_end() == s1
+    with pytest.raises(L.CitamCapacityError):
+        eng.partition_pairs_device(buf.data_ptr(), max(0, n - 1), 2) if n else (_ for _ in ()).throw(L.CitamCapacityError(-3, ""))
+    eng.close()

@@ -58,7 +58,7 @@ def test_record_sizes_match_header():
     assert L.BOUNDARY.itemsize == 56 and L.DOOR.itemsize == 32 and L.PAIR.itemsize == 24
     assert L.COORD.itemsize == 24 and L.CONTACT.itemsize == 12
     assert ctypes.sizeof(L.Config) == 56 and ctypes.sizeof(L.Counters) == 72 and ctypes.sizeof(L.Stats) == 48
-    assert "#define CITAM_ABI_VERSION 1" in hdr
+    assert "#define CITAM_ABI_VERSION %d" % L.ABI_VERSION in hdr
 
 
 def test_library_exports_every_declared_symbol():
@@ -69,7 +69,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.citam_abi_version() == 1
+    assert lib.citam_abi_version() == L.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback_without_device():
