@@ -7,17 +7,25 @@ Contract (see the task's bench section):
                                                            path on the host cores (same JSON)
 
 Workload (default `config3`, the shape BASELINE.json's target is quoted on): synthetic 10-floor
-facility, 10^6 agents, 3 shifts, T = 28 800 one-second steps (citam_b200/synthetic.py).  One
-bench "step" = one *time block* of `--block` simulation steps over ALL agents; the K timed
-blocks are spread evenly over the day so that the mix of empty / busy hours is the whole-day
-mix.  With N ranks every rank runs its own K blocks (time-block sharding, SURVEY.md §8e: no
-data-path collective; weak scaling) and the value is all ranks' agent-steps / max-over-ranks time.
+facility, 10^6 agents, 3 shifts, T = 28 800 one-second steps (citam_b200/synthetic.py).
+
+--mode day (default)  One bench "step" = ONE WHOLE SIMULATED DAY: the tables are cleared, all T
+  steps run over all agents, and the end-of-run reduction and the statistics are computed -- all
+  inside the timed region.  With N ranks the day is cut into N contiguous time ranges, one per rank
+  (time sharding; STRONG scaling: the total work is fixed), and the final exchange
+  -- NCCL all-reduce of the per-agent counters and the coordinate histogram, all-to-all of the
+  hash-partitioned pair table, device merge -- is part of the timed day.  value = K * N_agents * T /
+  max-over-ranks time.
+--mode blocks  One bench step = one time block of `--block` simulation steps; every rank runs its
+  own K blocks spread over the day (weak scaling, no data-path collective) -- the round-1 figure.
 
   value     inputs resident in HBM (itinerary store loaded before the timed region)
-  e2e       each block's itinerary slice copied from pinned host memory through the C ABI,
-            the block run, and its per-agent result read back, all inside the timed region
+  e2e       the same through the C ABI from HOST buffers: every step uploads the itinerary store from
+            pinned host memory (citam_load_itineraries), runs, and reads the per-agent result back
   roofline  dominant kernel (by summed CUDA-event time, measured in the timed region):
             algorithmic bytes = 12 B/agent-step + 64 B/contact-step
+  finalize  (day mode, once, after the timed days) compaction + device radix sort of the pair table
+            into first-contact order, and one device-to-host export of it (`e2e_with_results`)
 """
 from __future__ import annotations
 
@@ -35,7 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-RESET_EVERY = 40  # bench blocks between table resets (default runs never reach it)
+PROFILE_CSV = "r2_ncu_full_top_kernels.csv"
 METRIC = "agent-steps/sec incl. contact detection"
 UNIT = "agent-steps/s"
 
@@ -46,7 +54,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="day", choices=["day", "blocks"])
     ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config5", "tiny"])
+    ap.add_argument("--no-finalize", action="store_true", help="skip the once-only sorted export after the timed days")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check before timing (N > 1)")
     ap.add_argument("--agents", type=int, default=0, help="override the workload's agent count")
     ap.add_argument("--block", type=int, default=0, help="simulation steps per bench step (0 = auto)")
     ap.add_argument("--seed", type=int, default=0)
@@ -77,8 +88,8 @@ def profiled_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), or None."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_top_kernels.csv")
-    names = {"accumulate": "k_accumulate", "pairs": "k_pairs_changed", "expand_bin": "k_expand_bin"}
+    path = os.path.join(ROOT, "profiles", PROFILE_CSV)
+    names = {"accumulate": "k_accumulate", "pairs": "k_pairs_changed", "expand_bin": "k_expand_bin", "scatter": "k_scatter"}
     if not os.path.isfile(path) or kernel not in names:
         return None
     rows = list(csv.reader(open(path)))
@@ -244,10 +255,41 @@ def time_faithful_port(fac, seg_off, segs, p, D, n_sub=1500, steps=12):
             "sample": "the first %d agents x %d steps in the middle of the first shift (%.2f s)" % (n, steps, dt)}
 
 
+def workload_config(args, p, block):
+    """The `config` object: identical for the B200 arm and the reference arm of one mode."""
+    T = p["total_timesteps"]
+    cfg = {
+        "workload": "%s: synthetic %d-floor facility, %d agents, %d shift(s), T=%d 1-s steps, contact distance 6.0"
+        % (args.workload, p["n_floors"], p["n_agents"], p["n_shifts"], T),
+        "mode": args.mode,
+        "n_agents": p["n_agents"],
+    }
+    if args.mode == "day":
+        cfg.update({
+            "bench_step": "one whole simulated day: %d steps over all agents from cleared tables, incl. the end-of-run "
+                          "reduction and statistics" % T,
+            "agent_steps_per_bench_step": p["n_agents"] * T,
+            "sharding": "contiguous time ranges, one per rank; final exchange (all-reduce + all-to-all + merge) inside the step",
+            "l2": "inputs larger than L2 (each launch group streams > 1 GB of per-step records)"
+            if p["n_agents"] * 64 * 16 > 2e8 else "working set may fit L2 (small workload)",
+        })
+    else:
+        cfg.update({
+            "bench_step": "one time block of %d simulation steps over all agents; blocks spread evenly over the day" % block,
+            "block_steps": block,
+            "sharding": "time blocks per rank, no data-path collective",
+            "l2": "inputs larger than L2 (each block streams > 1 GB of per-step records)" if p["n_agents"] * block * 12 > 2e8
+            else "working set may fit L2 (small workload)",
+        })
+    return cfg
+
+
 def run_reference(args):
     """`--impl reference`: rank 0 times the CPU restatement (the upstream reference is pure
     Python + scipy and cannot travel to the GPU box; oracle/grid_oracle.c restates its path and
-    is pinned to it by tests/test_oracle_golden.py).  Other ranks exit 0 without work."""
+    is pinned to it by tests/test_oracle_golden.py).  Other ranks exit 0 without work.
+    Every bench step is a bounded sample of the arm's workload: one short time block per host
+    thread, blocks spread over the day (a whole day would take ~15 minutes of CPU time)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -255,50 +297,83 @@ def run_reference(args):
     D = 6.0
     g, threads = cpu_oracle(fac, seg_off, segs, p, D)
     T = p["total_timesteps"]
-    # bounded sample per bench step: one short time block per thread
-    per = 4  # simulation steps per thread and bench step (plus the one-step halo each thread evaluates)
+    block = args.block or auto_block(p)
+    per = 32 if p["n_agents"] <= 100_000 else 8  # simulation steps per thread and bench step (+ a one-step halo each)
     steps_each = max(2, per * threads)
     starts_w = block_starts(T, steps_each, max(1, args.warmup), 0, 1, offset=7)
     starts = block_starts(T, steps_each, args.steps, 0, 1)
     time_cpu_sample(g, threads, starts_w[: max(1, min(args.warmup, 1))], steps_each)
     units, dt = time_cpu_sample(g, threads, starts, steps_each)
     v = units / dt
-    sample = "%d blocks x %d simulation steps x %d agents, blocks spread over the day" % (len(starts), steps_each, g.n_agents)
+    sample = "%d samples x %d simulation steps x %d agents (%d steps per thread + halo), spread over the day" % (
+        len(starts), steps_each, g.n_agents, per)
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.mode == "day" else "weak", "vs_baseline": None,
         "dtype": "i32 positions, f64 distance predicate", "data": "synthetic", "impl": "reference",
-        "config": workload_config(args, p, steps_each),
+        "config": workload_config(args, p, block),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "oracle/grid_oracle.c (grid restatement of the reference path, OpenMP time blocks); the upstream "
-                "reference itself is single-threaded O(N^2) Python/scipy and cannot hold this N",
+                "reference itself is single-threaded O(N^2) Python/scipy and cannot hold this N; each bench step is a "
+                "bounded sample of the workload, ms_per_step is the sample's time",
     }
     print(json.dumps(line), file=_OUT, flush=True)
-
-
-def workload_config(args, p, block):
-    return {
-        "workload": "%s: synthetic %d-floor facility, %d agents, %d shift(s), T=%d 1-s steps, contact distance 6.0"
-        % (args.workload, p["n_floors"], p["n_agents"], p["n_shifts"], p["total_timesteps"]),
-        "bench_step": "one time block of %d simulation steps over all agents; blocks spread evenly over the day" % block,
-        "block_steps": block,
-        "n_agents": p["n_agents"],
-        "sharding": "time blocks per rank, no data-path collective",
-        "l2": "inputs larger than L2 (each block streams > 1 GB of per-step records)" if p["n_agents"] * block * 12 > 2e8
-        else "working set may fit L2 (small workload)",
-    }
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def default_pair_cap(args, p, world):
+    if args.pair_cap_log2:
+        return 1 << args.pair_cap_log2
+    N = p["n_agents"]
+    if args.mode == "blocks":
+        return int(min(1 << 31, max(1 << 22, 2048 * N)))
+    # whole day: ~1 700 distinct partners per agent and day on these crowded floors (measured, config 3);
+    # a rank's table holds its own range's pairs before the exchange and its share of all pairs after it
+    est = {"config5": 4096}.get(args.workload, 2048) * N
+    per_rank = est if world == 1 else max(est // world * 2, est // 2)
+    cap = 1 << 22
+    while cap < 2 * per_rank:
+        cap <<= 1
+    return int(min(cap, 1 << 32))
+
+
+def rows_sorted(buf, n, window=1 << 25):
+    """citam_pair rows {a1 | a2 << 32, first_step | n_events << 32, duration} as int64 triples: strictly increasing
+    in (first_step, a1, a2)?  Checked on the device, window by window."""
+    ok = True
+    for lo in range(0, max(0, n - 1), window):
+        hi = min(n, lo + window + 1)
+        key = buf[lo:hi, 1] & 0xFFFFFFFF
+        a1, a2 = buf[lo:hi, 0] & 0xFFFFFFFF, (buf[lo:hi, 0] >> 32) & 0xFFFFFFFF
+        lt = (key[:-1] < key[1:]) | ((key[:-1] == key[1:]) & ((a1[:-1] < a1[1:]) | ((a1[:-1] == a1[1:]) & (a2[:-1] < a2[1:]))))
+        ok = ok and bool(lt.all().item())
+    return ok
+
+
+def mgpu_parity(rank, world, local):
+    """N > 1: the sharded run + device exchange against the C oracle, table for table, before any timing."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import mgpu_check
+
+        mgpu_check.check(None, 4, world, rank, local)
+        mgpu_check.check(173, 5, world, rank, local)
+        return True
+    except AssertionError as e:
+        log("multi-GPU parity FAILED on rank %d: %s" % (rank, e))
+        return False
+
+
 def run_b200(args):
     import torch
 
-    from citam_b200 import _lib as L
-    from citam_b200 import itinerary as itin
+    from citam_b200 import distributed as DD
+    from citam_b200 import synthetic as S
     from citam_b200.engine import DeviceEngine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -312,71 +387,130 @@ def run_b200(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # first collectives on a cold communicator cost tens of ms: warm it with the message sizes used later
+        w = torch.zeros(1 << 24, dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            dist.all_reduce(w)
+            dist.all_to_all_single(torch.empty_like(w), w)
+        torch.cuda.synchronize()
+        del w
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        ok = mgpu_parity(rank, world, local)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity = bool(t.item())
+        log("multi-GPU parity vs oracle/grid_oracle.c:", parity)
 
     fac, seg_off, segs, p = build_workload(args)
-    log("workload built:", len(segs), "segments")
+    shape = S.activity(seg_off, segs, p["total_timesteps"])
+    log("workload built:", len(segs), "segments", shape)
     N, T, D = p["n_agents"], p["total_timesteps"], 6.0
     block = args.block or auto_block(p)
     K, W = args.steps, max(3, args.warmup)
 
-    pair_cap = int(min(1 << 31, max(1 << 22, 2048 * N)))
-    if args.pair_cap_log2:
-        pair_cap = 1 << args.pair_cap_log2
+    pair_cap = default_pair_cap(args, p, world)
     coord_cap = int(min(1 << 27, max(1 << 22, 64 * N)))
     eng = DeviceEngine(N, p["n_floors"], D, device=local, pair_capacity=pair_cap, coord_capacity=coord_cap,
                        steps_per_chunk=args.chunk, timing=True)
     eng.load_geometry(fac.geometry)
     eng.load_segments(seg_off, segs)
-    log("engine loaded; block", block, "K", K, "W", W)
-
-    starts_w = block_starts(T, block, W, rank, world, offset=3)
-    starts = block_starts(T, block, K, rank, world)
+    log("engine loaded; mode", args.mode, "K", K, "W", W, "pair table 2^%d slots" % (pair_cap.bit_length() - 1))
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        return float(t_all.item())
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    sharded = DD.ShardedRun(eng, T) if dist is not None else None
+    t_lo, t_hi = DD.plan_range(T, world, rank)
+    phase = {"run_ms": 0.0, "exchange_ms": 0.0}
+    last = {}
+
+    # ---- one bench step ------------------------------------------------------------------------
+    if args.mode == "day":
+        def step(k, timed=False):
+            eng.reset()
+            if timed:
+                ev[2].record()
+            eng.run(t_lo, t_hi)
+            if timed:
+                ev[3].record()
+            last["sums"] = sharded.reduce() if sharded is not None else eng.statistics_sums()
+            if timed:
+                torch.cuda.synchronize()
+                phase["run_ms"] += ev[2].elapsed_time(ev[3])
+        units_rank = K * N * (t_hi - t_lo)
+        units_all = K * N * T
+        steps_w = list(range(W))
+        steps_k = list(range(K))
+    else:
+        starts_w = block_starts(T, block, W, rank, world, offset=3)
+        starts = block_starts(T, block, K, rank, world)
+
+        def step(s, timed=False):
+            eng.run(s, s + block)
+        units_rank = K * block * N
+        units_all = units_rank * world
+        steps_w, steps_k = starts_w, starts
+
     # ---- value: itineraries resident in HBM -------------------------------------------------
-    for s in starts_w:
-        eng.run(s, s + block)
+    for s in steps_w:
+        step(s)
     torch.cuda.synchronize()
     c0 = eng.counters()
     tm0 = eng.timings()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for k, s in enumerate(starts):
-        if k and k % RESET_EVERY == 0:
-            eng.reset()  # keeps the pair table's load bounded on very long runs (inside the timed region)
-        eng.run(s, s + block)
-    ev1.record()
+    ev[0].record()
+    for s in steps_k:
+        step(s, timed=True)
+    ev[1].record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = ev[0].elapsed_time(ev[1])
     clk = clocks.stop()
     c1 = eng.counters()
     tm1 = eng.timings()
-    t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    ms_max = float(t_all.item())
-    units_rank = K * block * N
-    value = units_rank * world / (ms_max * 1e-3)
-    if K > RESET_EVERY:  # counters were cleared on the way: count from the last reset, scaled to K blocks
-        tail = K - (K - 1) // RESET_EVERY * RESET_EVERY
-        c0 = {k: (v if k == "kernel_launches" else 0) for k, v in c0.items()}
-        c1 = {k: (v * K // tail if k in ("contact_steps", "pair_tests", "contact_runs") else v) for k, v in c1.items()}
-    contacts = c1["contact_steps"] - c0["contact_steps"]
-    pair_tests = c1["pair_tests"] - c0["pair_tests"]
-    launches = c1["kernel_launches"] - c0["kernel_launches"]
-    runs = c1["contact_runs"] - c0["contact_runs"]
-
-    log("timed region done: %.1f ms, contacts %d, counters %s" % (ms, contacts, c1))
+    ms_max = max_over_ranks(ms)
+    value = units_all / (ms_max * 1e-3)
+    if args.mode == "day":
+        # counters are cleared by every day's reset: c1 is the last day's (this rank's range)
+        contacts, pair_tests, runs = (K * c1[k] for k in ("contact_steps", "pair_tests", "contact_runs"))
+        launches = c1["kernel_launches"] - c0["kernel_launches"]  # host-side count, not cleared by the resets
+    else:
+        contacts = c1["contact_steps"] - c0["contact_steps"]
+        pair_tests = c1["pair_tests"] - c0["pair_tests"]
+        launches = c1["kernel_launches"] - c0["kernel_launches"]
+        runs = c1["contact_runs"] - c0["contact_runs"]
+    log("timed region done: %.1f ms (max over ranks %.1f), contact-steps on this rank %d, counters %s" % (ms, ms_max, contacts, c1))
     if c1["overflow"]:
         raise SystemExit("bench.py: a device table overflowed (flags %d); the timed numbers are void - raise the capacities"
                          % c1["overflow"])
+    day = None
+    if args.mode == "day":
+        sums = last["sums"]
+        day = {
+            "day_s": ms_max * 1e-3 / K,
+            "run_ms_per_day": phase["run_ms"] / K,
+            "exchange_and_statistics_ms_per_day": (ms - phase["run_ms"]) / K,
+            "pairs_total": sums["n_pairs"], "total_contact_seconds": sums["total_duration"],
+            "pairs_on_rank0_after_exchange": c1["pair_slots_used"],
+            "pair_table_load_factor": c1["pair_slots_used"] / pair_cap,
+            "reset_included": True,
+        }
+        if sharded is not None:
+            day["exchange"] = dict(sharded.info)
+            day["limiting_collective"] = ("all-to-all of pair records (24 B each) by hash(a1,a2) mod %d: %.2f GB sent by rank 0"
+                                          % (world, sharded.info.get("a2a_bytes_sent", 0) / 1e9))
     # ---- roofline of the dominant kernel -----------------------------------------------------
     peak, peak_src = peaks()
     kern = {}
@@ -384,84 +518,98 @@ def run_b200(args):
         b = tm0.get(k, {"ms": 0.0, "launches": 0})
         if v["launches"] > b["launches"]:
             kern[k] = {"ms": v["ms"] - b["ms"], "launches": v["launches"] - b["launches"]}
-    dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+    step_kinds = [k for k in kern if k in ("expand_bin", "scan", "scatter", "pairs", "accumulate")]
+    dom = max(step_kinds, key=lambda k: kern[k]["ms"]) if step_kinds else None
     roof = None
     if dom:
-        alg_bytes = 12.0 * units_rank + 64.0 * contacts  # whole step
+        alg_bytes = 12.0 * units_rank + 64.0 * contacts  # whole step, this rank's share
         # the dominant kernel's own share of it: k_accumulate owns the 64 B per contact-step,
         # the position kernels the 12 B per agent-step
         own = 64.0 * contacts if dom == "accumulate" else 12.0 * units_rank
         per_launch = own / kern[dom]["launches"]
         avg_ms = kern[dom]["ms"] / kern[dom]["launches"]
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
+        run_ms = phase["run_ms"] if args.mode == "day" else ms
         roof = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": profiled_traffic(dom) if args.workload == "config3" and not args.agents else None, "traffic_source": "profiles/r1_ncu_full_top_kernels.csv (one launch, 64 steps x 1e6 agents)",
+            "traffic": profiled_traffic(dom) if args.workload == "config3" and not args.agents else None,
+            "traffic_source": "profiles/%s (one launch of the same build, 64 steps x 1e6 agents)" % PROFILE_CSV,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
             "algorithmic_bytes_rule": "k_accumulate: 64 B x contact-steps; expand/scatter/pairs: 12 B x agent-steps; whole step: both",
-            "kernel_share_of_step": kern[dom]["ms"] / ms,
+            "kernel_share_of_step": kern[dom]["ms"] / run_ms,
             "kernels_ms": {k: round(v["ms"], 3) for k, v in kern.items()},
-            "whole_step_achieved": alg_bytes / (ms * 1e-3) / 1e9, "whole_step_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak,
+            "kernels_note": "CUDA-event times per kernel kind; k_accumulate runs on a side stream and overlaps the next "
+                            "chunk's build, so the kinds do not add up to the step",
+            "whole_step_achieved": alg_bytes / (run_ms * 1e-3) / 1e9, "whole_step_frac": alg_bytes / (run_ms * 1e-3) / 1e9 / peak,
         }
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------
     e2e = None
+    e2e_res = None
     if not args.no_e2e:
-        slices = []
-        for s in starts_w[:2] + starts:
-            so, sg = itin.slice_segments(seg_off, segs, s - 1, s + block)
-            so_p = torch.from_numpy(so).pin_memory()
-            sg_p = torch.from_numpy(sg.view(np.uint8)).pin_memory()
-            slices.append((s, so_p, sg_p, len(sg)))
+        so_p = torch.from_numpy(np.ascontiguousarray(seg_off, np.int64)).pin_memory()
+        sg_p = torch.from_numpy(np.ascontiguousarray(segs).view(np.uint8)).pin_memory()
         out_dur = torch.empty(N, dtype=torch.int64).pin_memory()
-        eng.reset()
+        h2d_step = so_p.numel() * 8 + sg_p.numel()
 
-        def e2e_block(s, so_p, sg_p, nseg):
-            eng.load_segments_raw(so_p.data_ptr(), sg_p.data_ptr(), nseg)
-            eng.run(s, s + block)
+        def e2e_step(s):
+            eng.load_segments_raw(so_p.data_ptr(), sg_p.data_ptr(), len(segs))
+            step(s)
             eng.agent_durations_into(out_dur.data_ptr())
 
-        for sl in slices[:2]:
-            e2e_block(*sl)
+        if args.mode == "blocks":
+            eng.reset()
+        for s in steps_w[:2]:
+            e2e_step(s)
         barrier()
-        ev0.record()
-        h2d = 0
-        for sl in slices[2:]:
-            e2e_block(*sl)
-            h2d += sl[1].numel() * 8 + sl[2].numel()
-        ev1.record()
+        ev[0].record()
+        for s in steps_k:
+            e2e_step(s)
+        ev[1].record()
         barrier()
-        ms_e = ev0.elapsed_time(ev1)
-        t_all = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        ms_e = max_over_ranks(ev[0].elapsed_time(ev[1]))
         e2e = {
-            "value": units_rank * world / (float(t_all.item()) * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": N * 8,
-            "api": "citam_load_itineraries(block slice, pinned host) + citam_run(block) + citam_export_agent_durations",
+            "value": units_all / (ms_e * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": N * 8,
+            "api": "citam_load_itineraries(whole store, pinned host) + " + (
+                "citam_reset + citam_run(this rank's range) + final exchange + citam_statistics" if args.mode == "day"
+                else "citam_run(block)") + " + citam_export_agent_durations",
         }
-        eng.load_segments(seg_off, segs)
+        log("e2e done: %.1f ms" % ms_e)
 
-    log("e2e done")
-    # ---- end-of-run reduction (multi-GPU only; outside the per-step timing) ---------------------------
-    final_reduce_ms = None
-    if dist is not None:
-        ptr, n_el = eng.agent_durations_device()
-
-        class _Holder:
-            __cuda_array_interface__ = {"shape": (n_el,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-
-        tdur = torch.as_tensor(_Holder(), device="cuda")
-        sums = eng.statistics_sums()
-        tsum = torch.tensor([sums["total_duration"], sums["n_pairs"]], dtype=torch.int64, device="cuda")
-        barrier()
-        ev0.record()
-        dist.all_reduce(tdur)
-        dist.all_reduce(tsum)
-        ev1.record()
-        torch.cuda.synchronize()
-        final_reduce_ms = ev0.elapsed_time(ev1)
+    # ---- finalize: the pair table in first-contact order (once; day mode) ---------------------------
+    fin = None
+    if args.mode == "day" and not args.no_finalize:
+        try:
+            n_pairs = eng.pair_count()
+            buf = torch.empty((max(1, n_pairs), 3), dtype=torch.int64, device="cuda")
+            barrier()
+            ev[0].record()
+            got = eng.export_pairs_device(buf.data_ptr(), n_pairs)
+            ev[1].record()
+            torch.cuda.synchronize()
+            fin = {"finalize_ms": max_over_ranks(ev[0].elapsed_time(ev[1])), "pairs_sorted_on_this_rank": int(got),
+                   "what": "compaction of the pair table + device radix sort by (first contact step, a1, a2) into a device buffer"}
+            fin["sorted_ok"] = rows_sorted(buf, int(got))
+            if world == 1 and not args.no_e2e and got * 24 < 48e9:
+                host = torch.empty((max(1, got), 3), dtype=torch.int64).pin_memory()
+                eng.reset()
+                barrier()
+                ev[0].record()
+                e2e_step(0)
+                got2 = eng.export_pairs_device(buf.data_ptr(), n_pairs)
+                host[:got2].copy_(buf[:got2], non_blocking=True)
+                ev[1].record()
+                torch.cuda.synchronize()
+                ms_r = ev[0].elapsed_time(ev[1])
+                e2e_res = {"value": N * T / (ms_r * 1e-3), "unit": UNIT, "d2h_bytes": int(got2) * 24 + N * 8,
+                           "what": "one e2e day + the sorted pair table copied to pinned host memory"}
+                del host
+            del buf
+        except Exception as e:  # out of memory on the biggest tables: the timed numbers above stand
+            fin = {"finalize_ms": None, "error": str(e)[:200]}
+        log("finalize:", fin)
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
@@ -480,13 +628,16 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "i32 positions, f64 distance predicate", "data": "synthetic",
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong" if args.mode == "day" else "weak",
+            "vs_baseline": None, "dtype": "i32 positions, f64 distance predicate", "data": "synthetic",
             "config": workload_config(args, p, block),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": int(launches),
-            "contact_steps_per_step": contacts / K, "contacts_per_agent_step": contacts / units_rank,
-            "pair_tests_per_s": pair_tests / (ms * 1e-3), "table_updates_per_contact_step": runs / max(1, contacts),
-            "final_reduce_ms": final_reduce_ms,
+            "active_fraction": shape["active_fraction"], "moving_fraction": shape["moving_fraction"],
+            "active_agent_steps_per_s": value * shape["active_fraction"],
+            "contacts_per_agent_step": contacts / max(1, units_rank),
+            "pair_tests_per_s": pair_tests / ((phase["run_ms"] if args.mode == "day" else ms) * 1e-3),
+            "table_updates_per_contact_step": runs / max(1, contacts),
+            "day": day, "finalize": fin, "e2e_with_results": e2e_res, "mgpu_parity": parity,
         }
         print(json.dumps(line), file=_OUT, flush=True)
     eng.close()

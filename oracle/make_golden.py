@@ -194,6 +194,8 @@ def case_basic(seed=0):
         os.chdir(cwd)
     sim = captured["sim"]
     save_case("basic_seed%d" % seed, sim, tmp, sim.total_timesteps, extra_loc_points=6000, seed=seed)
+    # the entry point's own files (main.py:420-433): pins `citam engine run` beyond the step loop
+    gz_copy(os.path.join(tmp, "policy.json"), os.path.join(GOLD, "basic_seed%d" % seed, "expected", "policy.json.gz"))
     return sim, tmp
 
 

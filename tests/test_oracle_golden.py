@@ -232,3 +232,39 @@ def test_unmodified_reference_still_reproduces_the_two_floor_fixture(tmp_path):
                "floor_1/contact_dist_per_coord.csv"]:
         with gzip.open(os.path.join(str(tmp_path), "twofloor", "expected", fn + ".gz"), "rb") as f:
             assert f.read() == expected(case, fn), fn
+
+
+def test_unmodified_reference_still_reproduces_the_basic_and_crafted_fixtures(tmp_path):
+    """Same for the other two cases: `run_simulation` on examples/basic_example under seed 0 (the
+    `citam engine run` code path, incl. policy.json) and the crafted itineraries fed through the
+    reference's own Simulation / CloseContactsCalculator."""
+    from oracle import refload
+
+    if not refload.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import gzip
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, os\n"
+        "sys.path.insert(0, %r)\n"
+        "import oracle.make_golden as g\n"
+        "g.GOLD = %r\n"
+        "os.makedirs(g.GOLD, exist_ok=True)\n"
+        "base, _ = g.case_basic(0)\n"
+        "g.case_crafted(base)\n" % (root, str(tmp_path))
+    )
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = ["pair_contact.csv", "contact_dist_per_agent.csv", "statistics.json", "trajectory.txt", "raw_contact_data.ccd",
+             "floor_0/contacts.txt", "floor_0/contact_dist_per_coord.csv"]
+    for name, extra in (("basic_seed0", ["policy.json"]), ("crafted", [])):
+        case = load_case(name)
+        for fn in files + extra:
+            with gzip.open(os.path.join(str(tmp_path), name, "expected", fn + ".gz"), "rb") as f:
+                assert f.read() == expected(case, fn), (name, fn)
+        z = np.load(os.path.join(str(tmp_path), name, "inputs.npz"))
+        for k, v in zip(("itin_off", "itin_x", "itin_y", "itin_floor"), case["packed"]):
+            assert (z[k] == v).all(), (name, k)
