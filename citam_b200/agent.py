@@ -13,12 +13,14 @@ class Agent:
 
     def step(self, locate=None) -> bool:
         """agent.py:67-109: take the next itinerary entry; a `None` entry changes nothing.
+        Returns upstream's `has_moved`: the entry differs from the current position or floor (so a
+        `None` entry counts as a move once the agent is placed, a repeated position does not).
         `locate(floor, x, y)` gives the space index (the device-built location table)."""
         xy, floor = self.schedule.get_next_position()
-        if xy is None:
-            return False
-        self.pos = (xy[0], xy[1])
-        self.current_floor = floor
-        if locate is not None:
-            self.current_location = locate(floor, xy[0], xy[1])
-        return True
+        has_moved = xy != self.pos or floor != self.current_floor
+        if xy is not None:
+            self.pos = xy
+            self.current_floor = floor
+            if locate is not None:
+                self.current_location = locate(floor, xy[0], xy[1])
+        return has_moved

@@ -259,17 +259,24 @@ class Simulation:
             json.dump(manifest, f, indent=4)
 
     def save_maps(self, work_directory) -> None:
-        """simulation.py:422-458: floor_k/map.svg (walls, `<g id="root">`, the upstream viewBox rule)."""
+        """simulation.py:422-458: floor_k/map.svg -- the floorplan's walls inside `<g id="root">` with
+        the upstream viewBox rule (citam_b200/svg.py writes what `export_world_to_svg` would)."""
         from . import svg
-        from .facility import geometry_from_facility
 
-        geom = geometry_from_facility(self.facility)
+        geom = None
         for f in range(self.facility.number_of_floors):
             d = os.path.join(work_directory, "floor_" + str(f))
             os.makedirs(d, exist_ok=True)
             fp = self.facility.floorplans[f]
-            svg.write_map_svg(svg.floor_walls(geom["floors"][f]), os.path.join(d, "map.svg"),
-                              [fp.minx - 50, fp.miny - 50, fp.maxx + 50, fp.maxy + 50])
+            if getattr(fp, "walls", None) is not None:
+                walls = svg.wall_paths_of_floorplan(fp)
+            else:
+                if geom is None:
+                    from .facility import geometry_from_facility
+
+                    geom = geometry_from_facility(self.facility)
+                walls = svg.floor_walls(geom["floors"][f])
+            svg.write_map_svg(walls, os.path.join(d, "map.svg"), [fp.minx - 50, fp.miny - 50, fp.maxx + 50, fp.maxy + 50])
 
     def save_schedules(self, work_directory) -> None:
         """simulation.py:460-486."""

@@ -14,8 +14,8 @@ of it, 48 x 96 rooms with a 6-unit door on the corridor wall, a few rooms per ba
 conference room / restroom / cafeteria.  The hallway graph links every corridor to the spine.
 
 Agents (office_schedule.py:108-110,499-593 in spirit): not in the facility until their shift's
-entry time; enter at the floor entrance (spine foot), walk axis-aligned integer steps at an
-integer pace to their desk, alternate stays and walks over `n_stops` destinations (desk,
+entry time; enter at the floor entrance (spine foot), walk axis-aligned integer steps at the
+reference's pace (2-6 ft/s = 24-72 drawing units per step at this facility's scale) to their desk, alternate stays and walks over `n_stops` destinations (desk,
 conference room, restroom, cafeteria, another office; a few per cent of the shared destinations
 are on another floor, reached by the stairs at the spine head), keeping to a personal lane in
 corridors and spine, then walk out to a parking point *outside every space* (location None), so that
@@ -39,6 +39,7 @@ SPINE_X0 = 12 + ROOMS_PER_ROW * ROOM_W           # 588
 SPINE_X1 = SPINE_X0 + SPINE_W                     # 612
 SPINE_XC = (SPINE_X0 + SPINE_X1) // 2             # 600
 FLOOR_H = 1200
+FEET = 12  # drawing units per foot (example facility: floorplan_scale = 1/12 ft per unit)
 STAIRS_Y = FLOOR_H - 10
 PARK_Y = -30
 
@@ -228,7 +229,9 @@ def _make_batch(fac, a0, a1, n_agents, T, n_shifts, seed, n_stops, entry_window,
 
     office = pick_room(KIND_OFFICE, floor)
     desk_x, desk_y = point_in(office)
-    pace = rng.integers(2, 6, n).astype(np.int64)
+    # office_schedule.py:423-441: a pace of 2-6 ft/s (normal around 4), divided by the floorplan scale;
+    # this facility is drawn like the example one, 12 drawing units to the foot: 24-72 units per step
+    pace = (FEET * np.clip(np.rint(rng.normal(4.0, 1.0, n)), 2, 6)).astype(np.int64)
     lane = rng.integers(-9, 10, n).astype(np.int32)  # personal lane in corridors (24 wide) and spine
     spine_x = (SPINE_XC + lane).astype(np.int32)
 

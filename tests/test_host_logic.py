@@ -143,22 +143,80 @@ def test_statistics_from_sums_matches_python_rounding():
 
 
 def test_svg_writers(tmp_path):
+    """Structure of map.svg / heatmap.svg as visualization.py:298-473 and
+    close_contacts_calculator.py:320-377 produce them."""
     import xml.etree.ElementTree as ET
 
     from citam_b200 import svg
 
     c = load_case("twofloor")
     walls = svg.floor_walls(c["geometry"]["floors"][0])
-    assert len(walls) > 10 and len({tuple(w) for w in walls}) == len(walls)
+    assert len(walls) > 10 and len(set(walls)) == len(walls) and all(w.startswith("M ") and " L " in w for w in walls)
     d = str(tmp_path)
     with pytest.raises(FileNotFoundError):
         svg.write_heatmap_svg({(1.0, 2.0): 3}, d, 6.0)
     svg.write_map_svg(walls, os.path.join(d, "map.svg"), [-50, -170, 400, 250])
     root = ET.parse(os.path.join(d, "map.svg")).getroot()
-    assert root.attrib["viewBox"] == "-50 -170 400 250" and root[0].attrib["id"] == "root" and len(root[0]) == len(walls)
+    assert root.attrib == {"baseProfile": "full", "height": "100%", "version": "1.1", "viewBox": "-50 -170 400 250", "width": "100%"}
+    g = root[0]
+    assert len(root) == 1 and g.attrib == {"id": "root"} and g[0].tag.endswith("defs") and len(g) == 1 + len(walls)
+    # stroke width 3.0 * round(xmax / 1500, 1) (visualization.py:340-344, 358-361)
+    assert g[1].attrib == {"d": walls[0], "fill": "white", "stroke": "black", "stroke-width": str(3.0 * round(400 / 1500, 1))}
     svg.write_heatmap_svg({(1.0, 2.0): 3, (5.5, 7.0): 1}, d, 6.0)
     g = ET.parse(os.path.join(d, "heatmap.svg")).getroot()[0]
     circles = [e for e in g if e.tag.endswith("circle")]
-    assert len(circles) == 2 and circles[0].attrib["r"] == "6.0" and circles[0].attrib["filter"] == "url(#blurMe)"
-    assert circles[0].attrib["fill"] == svg.rdylgn_hex(0.0) == "#a50026" and svg.rdylgn_hex(1.0) == "#006837"
-    assert any(e.tag.endswith("filter") and e.attrib["id"] == "blurMe" for e in g)
+    assert len(circles) == 2 and circles[0].attrib["filter"] == "url(#blurMe)"
+    assert circles[0].attrib == {"cx": "1.0", "cy": "2.0", "r": "6.0", "fill": str(svg.rdylgn_rgba(0.0)), "fill-opacity": "0.2",
+                                 "filter": "url(#blurMe)"}
+    # upstream hands matplotlib's RGBA tuple to ElementTree as it is: the attribute is the tuple's string
+    assert circles[0].attrib["fill"] == "(0.6470588235294118, 0.0, 0.14901960784313725, 1.0)"
+    assert svg.rdylgn_hex(0.0) == "#a50026" and svg.rdylgn_hex(1.0) == "#006837" and svg.rdylgn_hex(0.5) == "#feffbe"
+    f = [e for e in g if e.tag.endswith("filter")]
+    assert len(f) == 1 and f[0].attrib == {"id": "blurMe", "width": "12.0", "height": "12.0", "x": "-100%", "y": "-100%"}
+    assert f[0][0].attrib == {"in": "SourceGraphic", "stdDeviation": str(6.0 * 0.4), "edgeMode": "duplicate"}
+
+
+def test_svg_files_against_the_references_own_example_files(tmp_path):
+    """examples/basic_example/floor_0/{map,heatmap}.svg were written by the real svgpathtools / svgwrite /
+    matplotlib stack: our map of the same facility is byte-identical up to the stroke width (the example
+    predates the viewBox-scaled width), and every heatmap circle gets the same fill string."""
+    import csv
+    import re
+
+    from oracle import refload
+
+    ex = os.path.join(refload.REFERENCE_ROOT, "examples", "basic_example")
+    if not refload.available() or not os.path.isfile(os.path.join(ex, "floor_0", "map.svg")):
+        pytest.skip("reference tree not present (GPU box)")
+    import subprocess
+    import sys
+
+    from citam_b200 import svg
+
+    script = (
+        "import sys, os\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import refload\n"
+        "refload.load()\n"
+        "os.chdir(%r)\n"
+        "from citam.engine.main import load_floorplans\n"
+        "from citam_b200 import svg\n"
+        "fp = load_floorplans('foo_facility', ['foo_floor'])[0]\n"
+        "svg.write_map_svg(svg.wall_paths_of_floorplan(fp), %r, [fp.minx - 50, fp.miny - 50, fp.maxx + 50, fp.maxy + 50])\n"
+        % (ROOT, ex, str(tmp_path / "map.svg"))
+    )
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ours = open(str(tmp_path / "map.svg")).read()
+    theirs = open(os.path.join(ex, "floor_0", "map.svg")).read()
+    assert 'stroke-width="%s"' % (3.0 * round(1250.0 / 1500, 1)) in ours
+    assert ours.replace('stroke-width="%s"' % (3.0 * round(1250.0 / 1500, 1)), 'stroke-width="3.0"') == theirs
+    # heatmap colours
+    txt = open(os.path.join(ex, "floor_0", "heatmap.svg")).read()
+    circ = re.findall(r'<circle cx="([^"]+)" cy="([^"]+)" r="[^"]+" fill="([^"]+)"', txt)
+    rows = list(csv.reader(open(os.path.join(ex, "floor_0", "contact_dist_per_coord.csv"))))[1:]
+    cnt = {(float(a), float(b)): int(c) for a, b, c in rows}
+    assert len(circ) == len(cnt) > 100
+    mx = max(cnt.values())
+    for cx, cy, fill in circ:
+        assert str(svg.rdylgn_rgba(1.0 - cnt[(float(cx), float(cy))] * 1.0 / mx)) == fill
