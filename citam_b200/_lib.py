@@ -98,9 +98,9 @@ EXPORTS = [
     "citam_get_timings", "citam_agent_durations_device", "citam_merge_pairs", "citam_merge_coords",
     "citam_hist_device", "citam_export_pairs_device", "citam_export_coords_device", "citam_partition_pairs_device",
     "citam_clear_pairs", "citam_merge_pairs_device", "citam_statistics_begin", "citam_stats_arrays_device",
-    "citam_statistics_end",
+    "citam_statistics_end", "citam_statistics_counters",
 ]
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 
@@ -157,6 +157,7 @@ def load() -> C.CDLL:
         "citam_statistics_begin": (C.c_int, [vp]),
         "citam_stats_arrays_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), pu64]),
         "citam_statistics_end": (C.c_int, [vp, C.POINTER(Stats)]),
+        "citam_statistics_counters": (C.c_int, [vp, C.POINTER(Stats)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -76,6 +76,7 @@ struct FloorDev {
   int32_t minx, miny, W, H;  // lattice of the location table
   int32_t ncx, ncy;          // uniform grid over the same lattice
   int32_t cell_base;         // first cell id of this floor
+  int32_t dncx, dncy, dcell_base;  // the coarse grid (cells of kDynCellMul x cell) the walking agents are binned in
   int32_t n_spaces;
   const int16_t* lut;   // [H][W] space index, -1 = none; NULL = floor not loaded
   const uint32_t* adj;  // n_spaces*n_spaces bits, NULL = no hallway graph
@@ -160,11 +161,27 @@ struct Params {
   ContactRec* cbuf;  // per-chunk contact buffer, kSubBuffers equal parts (NULL: accumulate inline)
   unsigned long long cbuf_sub_cap;
   unsigned long long* cbuf_count;  // its kSubBuffers counters (stride kCounterStride)
-  unsigned long long* agent_dur;   // [N] contact-steps per agent
+  unsigned long long* agent_dur;   // [N] contact-steps (40 bits) | contact events << 40 per agent
   uint32_t* chg_list;   // [S][N] located agents whose state may differ from the step before
   uint32_t* chg_count;  // [S] x 32 (one counter per 128 bytes); NULL = lists not kept
+  // split pipeline (citam_run without the contact log): per chunk, an agent that stands in ONE
+  // zero-velocity segment from the halo step to the chunk's end is "static" -- binned once, in
+  // `scells`/`ssorted` (fine grid); everything else that is around is "dynamic": expanded, binned
+  // (coarse grid, rows of `cells`) and sorted per step (`rec`/`sorted` rows are then indexed by the
+  // dynamic index, not by the agent).  cls == NULL: every agent is expanded at every step.
+  int32_t dcell;            // coarse cell edge
+  uint32_t dcell_magic;
+  int32_t dtotal_cells, dcells_stride;
+  uint32_t* cls;            // [N] dynamic index | kClsStatic | kClsOut
+  int4* srec;               // [N] a static agent's record {xy, until, state word, rank in cell}
+  int4* ssorted;            // static agents in cell order {xy, agent, state word, until}
+  uint32_t* scells;         // [cells_stride] static cell counts -> starts
+  uint32_t* dyn_agent;      // [N] agent of dynamic index j
+  uint32_t* dyn_count;      // dynamic agents of this chunk
   DevCounters* ctr;
 };
+constexpr uint32_t kClsOut = 0xFFFFFFFFu, kClsStatic = 0xFFFFFFFEu;
+constexpr int kDynCellMul = 4;
 
 #define OVF_PAIR 1ULL
 #define OVF_COORD 2ULL
@@ -184,6 +201,8 @@ struct Params {
 constexpr int kMaxChunk = 1024;     // steps per launch group (12 bits in ContactRec.t_run: <= 4096)
 constexpr int kMaxRunLog2 = 20;     // a contact run is clipped to 2^20 steps: longer citam_run ranges are split
 constexpr int kMaxFloors = 63;
+constexpr int kAgentDurBits = 40;   // per-agent counter word: contact-steps | events << 40
+constexpr unsigned long long kAgentDurMask = (1ULL << kAgentDurBits) - 1ULL;
 __device__ __forceinline__ int32_t pack_fl(int floor, int loc, int changed = 1, int moving = 0) {
   if (floor < 0) return (int32_t)0x8000ffffu;
   return (int32_t)(((uint32_t)(moving & 1) << 30) | ((uint32_t)(floor & 0x3f) << 24) |
@@ -218,6 +237,10 @@ __device__ __forceinline__ int div_cell(const Params& p, int v) {
 }
 __device__ __forceinline__ int cell_of_xy(const Params& p, const FloorDev& fd, int32_t xy) {
   return fd.cell_base + div_cell(p, xy_y(xy)) * fd.ncx + div_cell(p, xy_x(xy));
+}
+__device__ __forceinline__ int div_dcell(const Params& p, int v) { return (int)__umulhi((uint32_t)v, p.dcell_magic); }
+__device__ __forceinline__ int dcell_of_xy(const Params& p, const FloorDev& fd, int32_t xy) {
+  return fd.dcell_base + div_dcell(p, xy_y(xy)) * fd.dncx + div_dcell(p, xy_x(xy));
 }
 
 // Per agent, the steps at which it can matter to the loop: before `x` it is not in the facility;
@@ -263,10 +286,10 @@ __global__ void k_validate_segments(const long long* seg_off, const citam_segmen
 // every 16-byte record store is coalesced over the 32 agents of a warp.
 // --------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int rows, int do_bin, int kRowsPerThread) {
-  int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= p.N) return;
-  int r0 = blockIdx.y * kRowsPerThread;
+// `slot`: the agent's index inside a record row (the agent itself, or its dynamic index);
+// `coarse`: bin into the coarse per-step grid of the split pipeline.
+__device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot, int t_first, int rows, int r0, int do_bin,
+                                            int kRowsPerThread, bool coarse) {
   int2 win = make_int2(INT_MIN, INT_MAX);
   if (do_bin && p.window != nullptr) {
     win = p.window[a];
@@ -287,6 +310,7 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
   if (c >= sb) s = __ldg(&p.segs[c]);
   if (c + 1 < se) next_t0 = __ldg(&p.segs[c + 1].x) & 0xffffff;
   int lastx = INT_MIN, lasty = INT_MIN, lastf = -1, loc = -1;
+  const int stride = coarse ? p.dcells_stride : p.cells_stride;
 #pragma unroll 1
   for (int r = 0; r < kRowsPerThread; ++r) {
     int row = r0 + r;
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
       s = __ldg(&p.segs[c]);
       next_t0 = (c + 1 < se) ? (__ldg(&p.segs[c + 1].x) & 0xffffff) : INT_MAX;
     }
-    size_t o = (size_t)row * p.N + a;
+    size_t o = (size_t)row * p.N + slot;
     if (t + 1 < win.x || t >= win.y) continue;  // outside the agent's window (see k_agent_windows)
     if (c < sb || t < 0) {
       p.rec[o] = make_int4(0, 0, pack_fl(-1, -1), 0);
@@ -322,8 +346,124 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
     const int32_t xy = (x - fd.minx) | ((y - fd.miny) << 16);
     uint32_t rk = 0;
     if (do_bin && row >= 1)
-      rk = atomicAdd(&p.cells[(size_t)(row - 1) * p.cells_stride + cell_of_xy(p, fd, xy)], 1u);
+      rk = atomicAdd(&p.cells[(size_t)(row - 1) * stride + (coarse ? dcell_of_xy(p, fd, xy) : cell_of_xy(p, fd, xy))], 1u);
     p.rec[o] = make_int4(xy, still ? next_t0 : t + 1, pack_fl(f, loc, changed, still ? 0 : 1), (int)rk);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int rows, int do_bin, int kRowsPerThread) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.N) return;
+  expand_rows(p, a, (size_t)a, t_first, rows, blockIdx.y * kRowsPerThread, do_bin, kRowsPerThread, false);
+}
+
+// ---- split pipeline -------------------------------------------------------------------------
+// Class of every agent for the chunk of S steps starting at tb (records cover tb-1 .. tb+S-1):
+//   static   one zero-velocity segment holds from tb-1 to the chunk's end, inside a space: its state
+//            is the same at every step (changed == 0 throughout): ONE record, one grid cell rank
+//   dynamic  anything else whose window meets the chunk: gets the next dynamic index
+//   out      not around (or standing outside every space for the whole chunk)
+__global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t c = kClsOut;
+  bool dyn = false;
+  if (a < p.N) {
+    const int2 win = p.window[a];
+    if (!(win.x > tb + S || win.y <= tb - 1)) {
+      const int t = tb - 1;
+      const long long sb = p.seg_off[a], se = p.seg_off[a + 1];
+      long long lo = sb, hi = se;  // first segment with t0 > t
+      while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        int t0 = __ldg(&p.segs[mid].x) & 0xffffff;
+        if (t0 <= t) lo = mid + 1; else hi = mid;
+      }
+      const long long ci = lo - 1;
+      dyn = true;
+      if (ci >= sb && t >= 0) {
+        const int4 s = __ldg(&p.segs[ci]);
+        const int next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
+        if (s.w == 0 && next_t0 >= tb + S) {
+          dyn = false;
+          const int f = (s.x >> 24) & 0xff;
+          const int loc = (f < p.F) ? lut_lookup(p.floors[f], s.y, s.z) : -1;
+          if (loc >= 0) {
+            const FloorDev& fd = p.floors[f];
+            const int32_t xy = (s.y - fd.minx) | ((s.z - fd.miny) << 16);
+            const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
+            p.srec[a] = make_int4(xy, next_t0, pack_fl(f, loc, 0, 0), (int)rk);
+            c = kClsStatic;
+          }
+        }
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, dyn);
+  if (m) {
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(p.dyn_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (dyn) {
+      c = base + __popc(m & ((1u << lane) - 1u));
+      p.dyn_agent[c] = (uint32_t)a;
+    }
+  }
+  if (a < p.N) p.cls[a] = c;
+}
+
+__global__ void __launch_bounds__(256) k_scatter_static(Params p) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.N || p.cls[a] != kClsStatic) return;
+  const int4 r = p.srec[a];
+  const uint32_t dest = p.scells[cell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
+  p.ssorted[dest] = make_int4(r.x, a, r.z, r.y);
+}
+
+// expansion of the dynamic agents only: work item = (row group, dynamic index), grid-stride
+__global__ void __launch_bounds__(128) k_expand_dyn(Params p, int t_first, int rows, int kRowsPerThread) {
+  const uint32_t Dn = *p.dyn_count;
+  const unsigned long long groups = (unsigned)((rows + kRowsPerThread - 1) / kRowsPerThread);
+  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < Dn * groups;
+       w += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t g = (uint32_t)(w / Dn), j = (uint32_t)(w - (unsigned long long)g * Dn);
+    expand_rows(p, (int)p.dyn_agent[j], (size_t)j, t_first, rows, (int)g * kRowsPerThread, 1, kRowsPerThread, true);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_dyn(Params p, int rows /* S */, int t_begin) {
+  const uint32_t Dn = *p.dyn_count;
+  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < (unsigned long long)Dn * rows;
+       w += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(w / Dn), j = (uint32_t)(w - (unsigned long long)row * Dn);
+    const uint32_t a = p.dyn_agent[j];
+    const int2 win = p.window[a];
+    const int t = t_begin + (int)row;
+    if (t < win.x || t >= win.y) continue;  // no record was written
+    const int4 r = p.rec[(size_t)(row + 1) * p.N + j];
+    if (!fl_located(r.z)) continue;
+    const uint32_t dest = p.cells[(size_t)row * p.dcells_stride + dcell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
+    p.sorted[(size_t)row * p.N + dest] = make_int4(r.x, (int)a, r.z, r.y);
+  }
+}
+
+// per step the dynamic agents whose state may have changed, in (coarse) cell order; on `all_row`
+// (the first step of a range) every located dynamic agent
+__global__ void __launch_bounds__(256) k_select_changed_dyn(Params p, int rows /* S */, int all_row) {
+  const int row = blockIdx.y;
+  if (row >= rows) return;
+  const int total = (int)p.cells[(size_t)row * p.dcells_stride + p.dtotal_cells];
+  const int lane = threadIdx.x & 31;
+  for (int q0 = blockIdx.x * blockDim.x; q0 < total; q0 += gridDim.x * blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    bool sel = false;
+    if (q < total) sel = row == all_row || fl_changed(p.sorted[(size_t)row * p.N + q].z);
+    unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (m == 0) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&p.chg_count[row * 32], (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (sel) p.chg_list[(size_t)row * p.N + base + __popc(m & ((1u << lane) - 1))] = (uint32_t)q;
   }
 }
 
@@ -586,12 +726,18 @@ __device__ __forceinline__ void pair_apply_acc(const Params& p, unsigned long lo
   }
 }
 
-// The same plus the contact-steps on both agents' counters (close_contacts_calculator.py:221-224):
-// the counter array is N x 8 bytes, L2-resident, so these two reductions cost no DRAM access.
+// The same plus both agents' counters (close_contacts_calculator.py:221-224): the counter array is
+// N x 8 bytes, L2-resident, so these two reductions cost no DRAM access.  One word per agent carries
+// its contact-steps (low 40 bits) and its number of contact events (high 24 bits), so the run's
+// statistics (contacts.py:185-294: events per agent, agents with contacts) need no pass over the pair
+// table.  citam_run keeps (n_agents - 1) x steps since the reset below 2^40 (the most contact-steps an
+// agent can collect); the event field is exact whenever the agent's contact-steps are < 2^24 (an event
+// has at least one step), which the statistics kernel checks before trusting it.
 __device__ __forceinline__ void pair_apply(const Params& p, unsigned long long h, unsigned long long old, uint32_t first,
                                            unsigned long long add_dur, unsigned long long add_nev, uint32_t a1, uint32_t a2) {
-  atomicAdd(&p.agent_dur[a1], add_dur);
-  atomicAdd(&p.agent_dur[a2], add_dur);
+  const unsigned long long w = add_dur | (add_nev << kAgentDurBits);
+  atomicAdd(&p.agent_dur[a1], w);
+  atomicAdd(&p.agent_dur[a2], w);
   pair_apply_acc(p, h, old, first, add_dur, add_nev);
 }
 
@@ -641,8 +787,16 @@ __device__ __forceinline__ bool contact_eval(const Params& p, const int4& r1, co
   if (!within_xy(r1.x, r2.x, p)) return false;
   return loc_rule(p.floors[fl1], fl_loc(r1.z), fl_loc(r2.z));
 }
-__device__ __forceinline__ bool contact_prev(const Params& p, size_t prow_off, uint32_t a1, uint32_t a2) {
-  return contact_eval(p, p.rec[prow_off + a1], p.rec[prow_off + a2]);
+// An agent's record at the step before row `t_rel + 1` of the chunk (row t_rel; row 0 = halo step)
+__device__ __forceinline__ int4 prev_rec(const Params& p, uint32_t t_rel, uint32_t a) {
+  if (p.cls == nullptr) return p.rec[(size_t)t_rel * p.N + a];
+  const uint32_t c = p.cls[a];
+  if (c == kClsStatic) return p.srec[a];
+  if (c == kClsOut) return make_int4(0, 0, (int32_t)0x8000ffffu, 0);
+  return p.rec[(size_t)t_rel * p.N + c];
+}
+__device__ __forceinline__ bool contact_prev(const Params& p, uint32_t t_rel, uint32_t a1, uint32_t a2) {
+  return contact_eval(p, prev_rec(p, t_rel, a1), prev_rec(p, t_rel, a2));
 }
 
 // A contact found at step t that lasts `run` steps (both agents provably stay put for run-1
@@ -673,7 +827,7 @@ __device__ __forceinline__ void on_contact(const Params& p, uint32_t t, const in
     }
     // sub-buffer full: fall through and accumulate inline (k_accumulate clamps the count)
   }
-  if (late) was = contact_prev(p, (size_t)((int)t - p.chunk_begin) * p.N, a1, a2);
+  if (late) was = contact_prev(p, t - (uint32_t)p.chunk_begin, a1, a2);
   uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
   pair_upsert(p, a1, a2, first, run, was ? 0u : 1u);
   coord_upsert_rel(p, floor, ix, iy, (unsigned long long)run);
@@ -709,17 +863,18 @@ __device__ __forceinline__ uint32_t run_length(const Params& p, int until_a, int
 constexpr int kPairThreads = 256;
 constexpr int kWindow = 2560;  // records (40 KB)
 
-__global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, int rows /* S */, int aggregate) {
+__global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, int rows /* S */, int aggregate, int statics) {
   __shared__ int4 win[kWindow];
   __shared__ int s_w1;
   __shared__ int s_void;
   const int row = blockIdx.y;
-  const uint32_t* cs = p.cells + (size_t)row * p.cells_stride;
+  // statics: the chunk's static agents (split pipeline; one row, the range's first step)
+  const uint32_t* cs = statics ? p.scells : p.cells + (size_t)row * p.cells_stride;
   const int total = (int)cs[p.total_cells];
   const int w0 = blockIdx.x * kPairThreads;
   if (w0 >= total) return;  // whole block
   const int q0 = w0 + threadIdx.x;
-  const int4* srt = p.sorted + (size_t)row * p.N;
+  const int4* srt = statics ? p.ssorted : p.sorted + (size_t)row * p.N;
   if (threadIdx.x == 0) {
     s_w1 = w0;
     // results are void already when a table has overflowed: one read per block, the same answer for all its threads
@@ -914,10 +1069,176 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
           } else {  // sub-buffer full: apply inline (k_accumulate clamps the count)
             const ContactRec r = mine[j];
             const uint32_t rt = (uint32_t)p.chunk_begin + (r.t_run & 0xfffu), rrun = (r.t_run >> 12) + 1u;
-            bool was = contact_prev(p, (size_t)(r.t_run & 0xfffu) * p.N, r.a1, r.a2);
+            bool was = contact_prev(p, r.t_run & 0xfffu, r.a1, r.a2);
             uint32_t first = (!was || (int32_t)rt == p.range_begin) ? rt : NO_STEP;
             pair_upsert(p, r.a1, r.a2, first, rrun, was ? 0u : 1u);
             atomicAdd(p.hist + (r.bucket & 0x3fffffffu), (unsigned long long)rrun);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the batch's shared arrays are reused
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    tests += __shfl_down_sync(0xffffffffu, tests, d);
+    hits += __shfl_down_sync(0xffffffffu, hits, d);
+    runs += __shfl_down_sync(0xffffffffu, runs, d);
+  }
+  if (lane == 0 && (tests | hits)) {
+    atomicAdd(&p.ctr->pair_tests, tests);
+    if (hits) { atomicAdd(&p.ctr->contact_steps, hits); atomicAdd(&p.ctr->contact_runs, runs); }
+  }
+}
+
+// The same for the split pipeline: the changed agents of a step are all dynamic; each is tested
+// against the chunk's STATIC agents (3 x 3 fine cells of `scells` / `ssorted`: three ranges) and
+// against the step's DYNAMIC agents (3 x 3 coarse cells of the step's row of `cells` / `sorted`:
+// three more ranges) -- six contiguous ranges per agent, flattened over the batch as above.  A
+// static agent never owns a pair with a changed one; two dynamic agents: the lower id owns the
+// pair if the other one is changed too (on `all_row`, the first step of a range, every dynamic
+// agent counts as changed: that step owns every contact it finds, static-static pairs are k_pairs').
+__global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_begin, int rows /* S */, int all_row) {
+  __shared__ ContactRec hitbuf[kPC * kHitSlots];
+  __shared__ int4 s_me[kPC];
+  __shared__ int s_qs[6][kPC];
+  __shared__ int s_cum[5][kPC];  // ends of ranges 0..4 in the agent's candidate index space
+  __shared__ int s_off[kPC + 1];
+  __shared__ int s_warp[kPC / 32];
+  __shared__ int s_void;
+  const int row = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t n = p.chg_count[row * 32];
+  if (blockIdx.x * kPC >= n) return;
+  if (threadIdx.x == 0)
+    s_void = (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) != 0;
+  __syncthreads();
+  if (s_void) return;
+  const uint32_t* cs = p.scells;                                      // static starts (fine grid)
+  const uint32_t* cd = p.cells + (size_t)row * p.dcells_stride;       // this step's dynamic starts (coarse grid)
+  const int4* srt = p.sorted + (size_t)row * p.N;
+  const uint32_t t = (uint32_t)(t_begin + row);
+  const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
+  const bool buffered = p.cbuf != nullptr;
+  const bool all = row == all_row;
+  ContactRec* mine = hitbuf + threadIdx.x * kHitSlots;
+  unsigned long long tests = 0, hits = 0, runs = 0;
+  for (uint32_t base = blockIdx.x * kPC; base < n; base += gridDim.x * kPC) {
+    // ---- phase 1: one thread per agent describes its candidate ranges
+    const uint32_t idx = base + threadIdx.x;
+    int total = 0;
+    if (idx < n) {
+      const int4 me = srt[p.chg_list[(size_t)row * p.N + idx]];
+      const FloorDev& fd = p.floors[fl_floor(me.z)];
+      int len[6];
+      {
+        const int cx = div_cell(p, xy_x(me.x)), cy = div_cell(p, xy_y(me.x));
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
+        const int rb = fd.cell_base + cy * fd.ncx;
+        const bool up = cy + 1 < fd.ncy, dn = cy > 0;
+        const int rbu = up ? rb + fd.ncx : rb, rbd = dn ? rb - fd.ncx : rb;
+        const int q0 = (int)cs[rbd + x0], q1 = (int)cs[rb + x0], q2 = (int)cs[rbu + x0];
+        len[0] = dn ? (int)cs[rbd + x1 + 1] - q0 : 0;
+        len[1] = (int)cs[rb + x1 + 1] - q1;
+        len[2] = up ? (int)cs[rbu + x1 + 1] - q2 : 0;
+        s_qs[0][threadIdx.x] = q0; s_qs[1][threadIdx.x] = q1; s_qs[2][threadIdx.x] = q2;
+      }
+      {
+        const int cx = div_dcell(p, xy_x(me.x)), cy = div_dcell(p, xy_y(me.x));
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.dncx - 1);
+        const int rb = fd.dcell_base + cy * fd.dncx;
+        const bool up = cy + 1 < fd.dncy, dn = cy > 0;
+        const int rbu = up ? rb + fd.dncx : rb, rbd = dn ? rb - fd.dncx : rb;
+        const int q0 = (int)cd[rbd + x0], q1 = (int)cd[rb + x0], q2 = (int)cd[rbu + x0];
+        len[3] = dn ? (int)cd[rbd + x1 + 1] - q0 : 0;
+        len[4] = (int)cd[rb + x1 + 1] - q1;
+        len[5] = up ? (int)cd[rbu + x1 + 1] - q2 : 0;
+        s_qs[3][threadIdx.x] = q0; s_qs[4][threadIdx.x] = q1; s_qs[5][threadIdx.x] = q2;
+      }
+      s_me[threadIdx.x] = me;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) { total += len[r]; s_cum[r][threadIdx.x] = total; }
+      total += len[5];
+    }
+    // block exclusive scan of the candidate counts
+    int inc = total;
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += v;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += s_warp[w];
+    s_off[threadIdx.x] = woff + inc - total;
+    if (threadIdx.x == kPC - 1) s_off[kPC] = woff + inc;
+    __syncthreads();
+    const int P = s_off[kPC];
+    // ---- phase 2: one candidate test per thread and iteration
+    int nh = 0;
+    for (int pp = threadIdx.x; pp < P; pp += kPC) {
+      int lo = 0, hi = kPC;  // largest i with s_off[i] <= pp
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= pp) lo = mid; else hi = mid;
+      }
+      const int i = lo, k = pp - s_off[i];
+      int r = 0, kb = 0;  // range of candidate k and where that range begins
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int e = s_cum[q][i];
+        if (k >= e) { r = q + 1; kb = e; }
+      }
+      const int q = s_qs[r][i] + (k - kb);
+      const bool dyn_cand = r >= 3;
+      const int4 ot = dyn_cand ? srt[q] : p.ssorted[q];
+      const int4 me = s_me[i];
+      const int a = me.y;
+      if (dyn_cand) {
+        if (ot.y == a) continue;
+        if ((all || fl_changed(ot.z)) && ot.y < a) continue;  // that agent owns the pair
+      }
+      ++tests;
+      if (!within_xy(me.x, ot.x, p)) continue;
+      const FloorDev& fd = p.floors[fl_floor(me.z)];
+      if (fl_floor(ot.z) != fl_floor(me.z)) continue;  // cannot happen (cells are per floor); cheap guard
+      if (!loc_rule_ordered(fd, a, fl_loc(me.z), ot.y, fl_loc(ot.z))) continue;
+      const uint32_t run = run_length(p, me.w, ot.w, t);
+      hits += run;
+      ++runs;
+      if (buffered && nh < kHitSlots) {
+        ContactRec rec;
+        rec.a1 = (uint32_t)min(a, ot.y); rec.a2 = (uint32_t)max(a, ot.y);
+        rec.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
+        rec.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
+                       (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
+        mine[nh++] = rec;
+      } else {
+        on_contact(p, t, me, ot, run, false, sub, true);
+      }
+    }
+    if (buffered) {
+      // one reservation for the whole warp
+      int off = nh;
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, off, d);
+        if (lane >= d) off += v;
+      }
+      const int wtotal = __shfl_sync(0xffffffffu, off, 31);
+      if (wtotal > 0) {
+        unsigned long long wbase = 0;
+        if (lane == 31) wbase = atomicAdd(&p.cbuf_count[sub * kCounterStride], (unsigned long long)wtotal);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31) + (unsigned long long)(off - nh);
+        for (int j = 0; j < nh; ++j) {
+          if (wbase + j < p.cbuf_sub_cap) {
+            p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + wbase + j] = mine[j];
+          } else {  // sub-buffer full: apply inline (k_accumulate clamps the count)
+            const ContactRec rr = mine[j];
+            const uint32_t rt = (uint32_t)p.chunk_begin + (rr.t_run & 0xfffu), rrun = (rr.t_run >> 12) + 1u;
+            bool was = contact_prev(p, rr.t_run & 0xfffu, rr.a1, rr.a2);
+            uint32_t first = (!was || (int32_t)rt == p.range_begin) ? rt : NO_STEP;
+            pair_upsert(p, rr.a1, rr.a2, first, rrun, was ? 0u : 1u);
+            atomicAdd(p.hist + (rr.bucket & 0x3fffffffu), (unsigned long long)rrun);
           }
         }
       }
@@ -958,10 +1279,9 @@ __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
     bool was = r.bucket >> 31;
     int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
     const bool late = (r.bucket >> 30) & 1;
-    if (late) {
-      size_t prow = (size_t)t_rel * p.N;  // rec row holding step t-1
-      r1 = p.rec[prow + r.a1];
-      r2 = p.rec[prow + r.a2];
+    if (late) {  // both agents' records of step t-1
+      r1 = prev_rec(p, t_rel, r.a1);
+      r2 = prev_rec(p, t_rel, r.a2);
     }
     // the histogram reduction and the table probe are independent: issue both, then update
     atomicAdd(p.hist + (r.bucket & 0x3fffffffu), (unsigned long long)run);
@@ -1291,6 +1611,39 @@ __global__ void k_stats_agents(const uint32_t* agent_nev, const uint32_t* agent_
   }
 }
 
+// The same sums from the per-agent counter words alone (no pass over the table): events per agent
+// and has-contact flags into the two arrays, sums into stats[0] (contact-steps over agents = 2 x over
+// pairs), [2], [3], [4]; stats[5] = the largest per-agent contact-steps (the event field's guard).
+__global__ void k_stats_counters(const unsigned long long* agent_dur, uint32_t* agent_nev, uint32_t* agent_has, int N,
+                                 DevCounters* ctr) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long dur = 0, has = 0, nev = 0, mx = 0, mxd = 0;
+  if (a < N) {
+    const unsigned long long w = agent_dur[a];
+    dur = w & kAgentDurMask; nev = w >> kAgentDurBits; has = nev != 0; mx = nev; mxd = dur;
+    agent_nev[a] = (uint32_t)nev; agent_has[a] = (uint32_t)has;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    dur += __shfl_down_sync(0xffffffffu, dur, d);
+    has += __shfl_down_sync(0xffffffffu, has, d);
+    nev += __shfl_down_sync(0xffffffffu, nev, d);
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    mxd = max(mxd, __shfl_down_sync(0xffffffffu, mxd, d));
+  }
+  if ((threadIdx.x & 31) == 0 && dur) {
+    atomicAdd(&ctr->stats[0], dur);
+    atomicAdd(&ctr->stats[2], has);
+    atomicAdd(&ctr->stats[3], nev);
+    atomicMax(&ctr->stats[4], mx);
+    atomicMax(&ctr->stats[5], mxd);
+  }
+}
+
+__global__ void k_unpack_durations(const unsigned long long* agent_dur, int N, unsigned long long* out) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < N) out[a] = agent_dur[a] & kAgentDurMask;
+}
+
 // Records of another engine (rank) into this table.  Only the pair table is touched: per-agent
 // contact seconds are reduced separately (all-reduce of the counters), see the header.
 __global__ void k_merge_pairs(Params p, const citam_pair* in, unsigned long long n, int* bad) {
@@ -1357,6 +1710,15 @@ struct citam_engine {
   bool applied_pending[2] = {false, false};
   uint32_t* cells = nullptr;
   int4* sorted = nullptr;
+  // split pipeline: static agents' records and classes are read by k_accumulate too -> double-buffered
+  int4* srec_buf[2] = {nullptr, nullptr};
+  uint32_t* cls_buf[2] = {nullptr, nullptr};
+  int4* ssorted = nullptr;
+  uint32_t *scells = nullptr, *dyn_agent = nullptr, *dyn_count = nullptr;
+  int dtotal_cells = 0, dcells_stride = 4;
+  bool split = false;  // the chunk being processed uses the split pipeline
+  bool no_fast_stats = false;  // CITAM_NO_FAST_STATS=1: statistics always from the pass over the pair table (tests)
+  bool no_split = false;  // CITAM_NO_SPLIT=1: every agent is expanded and binned at every step (A/B measurements, tests)
 
   PairEntry* pairs = nullptr;
   unsigned long long pair_cap = 0;
@@ -1378,6 +1740,9 @@ struct citam_engine {
   uint32_t *chg_list = nullptr, *chg_count = nullptr, *part_sums = nullptr;
   unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
+  unsigned long long* dur_out = nullptr;  // unpacked contact seconds (export scratch)
+  bool counters_match = true;  // the per-agent counter words describe exactly the pairs in the table
+  unsigned long long steps_since_reset = 0;
   DevCounters* ctr_d = nullptr;
   int* flag_d = nullptr;  // scratch word for device-side validation
 
@@ -1504,6 +1869,13 @@ static Params make_params(citam_engine* e) {
   p.agent_dur = e->agent_dur;
   const bool agg = e->log_cap == 0;  // run aggregation (off when every contact-step is logged)
   p.chg_list = agg ? e->chg_list : nullptr; p.chg_count = agg ? e->chg_count : nullptr;
+  p.dcell = e->cell * kDynCellMul;
+  p.dcell_magic = (uint32_t)((1ULL << 32) / (unsigned)p.dcell) + 1u;
+  p.dtotal_cells = e->dtotal_cells; p.dcells_stride = e->dcells_stride;
+  if (e->split) {
+    p.cls = e->cls_buf[e->cur]; p.srec = e->srec_buf[e->cur];
+    p.ssorted = e->ssorted; p.scells = e->scells; p.dyn_agent = e->dyn_agent; p.dyn_count = e->dyn_count;
+  }
   p.ctr = e->ctr_d;
   return p;
 }
@@ -1516,6 +1888,9 @@ static void free_chunk(citam_engine* e) {
   cudaFree(e->cells);
   cudaFree(e->sorted); cudaFree(e->chg_list); cudaFree(e->chg_count); cudaFree(e->part_sums);
   e->chg_list = e->chg_count = e->part_sums = nullptr;
+  for (int b = 0; b < 2; ++b) { cudaFree(e->srec_buf[b]); cudaFree(e->cls_buf[b]); e->srec_buf[b] = nullptr; e->cls_buf[b] = nullptr; }
+  cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count);
+  e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -1534,6 +1909,16 @@ static int ensure_ready(citam_engine* e, int want_steps) {
     }
     e->total_cells = base;
     e->cells_stride = ((base + 1) + 3) & ~3;
+    int dbase = 0;
+    const int dcell = e->cell * kDynCellMul;
+    for (auto& f : e->floors_h) {
+      f.dncx = f.lut ? (f.W + dcell - 1) / dcell : 0;
+      f.dncy = f.lut ? (f.H + dcell - 1) / dcell : 0;
+      f.dcell_base = dbase;
+      dbase += f.dncx * f.dncy;
+    }
+    e->dtotal_cells = dbase;
+    e->dcells_stride = ((dbase + 1) + 3) & ~3;
     // dense per-coordinate histogram over every floor's half-unit lattice (contact positions are
     // midpoints of integer points); lattices beyond kDenseHistMax buckets use the hashed table.
     // Changing a floor's lattice drops the histogram's contents (documented in the header).
@@ -1582,6 +1967,14 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->chg_list, sizeof(uint32_t) * n * S));
   CK(cudaMalloc(&e->chg_count, sizeof(uint32_t) * 32 * S));
   CK(cudaMalloc(&e->part_sums, sizeof(uint32_t) * kMaxScanParts * S));
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&e->srec_buf[b], sizeof(int4) * n));
+    CK(cudaMalloc(&e->cls_buf[b], sizeof(uint32_t) * n));
+  }
+  CK(cudaMalloc(&e->ssorted, sizeof(int4) * n));
+  CK(cudaMalloc(&e->scells, sizeof(uint32_t) * (size_t)e->cells_stride));
+  CK(cudaMalloc(&e->dyn_agent, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->dyn_count, sizeof(uint32_t)));
   e->S = S;
   return CITAM_OK;
 }
@@ -1589,31 +1982,52 @@ static int ensure_ready(citam_engine* e, int want_steps) {
 static int pick_chunk(citam_engine* e, int steps) {
   if (e->cfg.steps_per_chunk > 0) return std::min(std::min(steps, e->cfg.steps_per_chunk), kMaxChunk);
   // ~64M agent-steps per launch group (3.3 GiB of per-step records), bounded by 1 GiB of histogram rows
-  long long by_agents = std::max(1LL, (64LL << 20) / std::max(1, e->N));
+  const bool split = e->log_cap == 0 && !e->no_split;
+  long long by_agents = std::max(1LL, ((split ? 256LL : 64LL) << 20) / std::max(1, e->N));
   long long by_cells = std::max(1LL, (1LL << 28) / std::max(4, e->cells_stride));
   long long s = std::min(by_agents, by_cells);
-  s = std::min<long long>(s, kMaxChunk);
+  // without the contact log (split pipeline) an agent is binned once per chunk if it stands still for
+  // the whole chunk: short chunks keep most agents in that class
+  s = std::min<long long>(s, e->log_cap == 0 ? 128 : kMaxChunk);
   s = std::max<long long>(s, 1);
   return (int)std::min<long long>(s, steps);
+}
+
+// per-row exclusive scan of `rows` histogram rows of n = cells + 1 words (stride words apart)
+static void launch_scan(citam_engine* e, uint32_t* cells, int stride, int n, int rows) {
+  Timed tm(e, CITAM_K_SCAN);
+  const int n4 = (n + 3) >> 2;
+  int parts = std::max(1, std::min(kMaxScanParts, std::min((296 + rows - 1) / rows, (n4 + 4095) / 4096)));
+  int part_len4 = (n4 + parts - 1) / parts;
+  parts = (n4 + part_len4 - 1) / part_len4;
+  k_scan<<<dim3(parts, rows), kScanThreads, 0, e->stream>>>(cells, stride, n, part_len4, e->part_sums);
+  if (parts > 1) {
+    e->launches++;
+    k_scan_add<<<dim3(parts - 1, rows), 256, 0, e->stream>>>(cells, stride, n, part_len4, e->part_sums);
+  }
+}
+
+// the chunk's contact buffer is applied on the side stream, overlapping the next chunk's build
+static int launch_accumulate(citam_engine* e, const Params& p, int t_begin) {
+  if (p.cbuf == nullptr) return CITAM_OK;
+  CK(cudaEventRecord(e->ev_built[e->cur], e->stream));
+  CK(cudaStreamWaitEvent(e->stream2, e->ev_built[e->cur], 0));
+  {
+    Timed tm(e, CITAM_K_ACCUMULATE, e->stream2, true);
+    k_accumulate<<<kSubBuffers * e->acc_blocks, 256, 0, e->stream2>>>(p, t_begin);
+    k_reset_cbuf<<<1, kSubBuffers, 0, e->stream2>>>(p.cbuf_count);
+    e->launches++;
+  }
+  CK(cudaEventRecord(e->ev_applied[e->cur], e->stream2));
+  e->applied_pending[e->cur] = true;
+  return CITAM_OK;
 }
 
 // bin (already done by caller) -> scan -> scatter -> pairs for `rows` steps starting at t_begin
 static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
   Params p = make_params(e);
   p.chunk_begin = t_begin;
-  {
-    Timed tm(e, CITAM_K_SCAN);
-    const int n4 = (e->total_cells + 1 + 3) >> 2;
-    int parts = std::max(1, std::min(kMaxScanParts, std::min((296 + rows - 1) / rows, (n4 + 4095) / 4096)));
-    int part_len4 = (n4 + parts - 1) / parts;
-    parts = (n4 + part_len4 - 1) / part_len4;
-    k_scan<<<dim3(parts, rows), kScanThreads, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
-                                                              e->part_sums);
-    if (parts > 1) e->launches++;
-    if (parts > 1)
-      k_scan_add<<<dim3(parts - 1, rows), 256, 0, e->stream>>>(e->cells, e->cells_stride, e->total_cells + 1, part_len4,
-                                                               e->part_sums);
-  }
+  launch_scan(e, e->cells, e->cells_stride, e->total_cells + 1, rows);
   const bool agg = p.chg_count != nullptr;
   // the first step of a range is evaluated in full (k_pairs); every other step through its changed agents
   const int row0 = (t_begin == e->range_begin) ? 1 : 0;
@@ -1632,7 +2046,7 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
     bool launched = false;
     if (!agg || row0 == 1) {
       dim3 g((e->N + 255) / 256, agg ? 1 : rows);
-      k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0);
+      k_pairs<<<g, 256, 0, e->stream>>>(p, t_begin, rows, agg ? 1 : 0, 0);
       launched = true;
     }
     if (agg && rows > row0) {
@@ -1641,19 +2055,53 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
       k_pairs_changed<<<g2, 256, 0, e->stream>>>(p, t_begin, row0, rows);
     }
   }
-  if (p.cbuf != nullptr) {
-    // the contact buffer is applied on the side stream, overlapping the next chunk's build
-    CK(cudaEventRecord(e->ev_built[e->cur], e->stream));
-    CK(cudaStreamWaitEvent(e->stream2, e->ev_built[e->cur], 0));
-    {
-      Timed tm(e, CITAM_K_ACCUMULATE, e->stream2, true);
-      k_accumulate<<<kSubBuffers * e->acc_blocks, 256, 0, e->stream2>>>(p, t_begin);
-      k_reset_cbuf<<<1, kSubBuffers, 0, e->stream2>>>(p.cbuf_count);
+  int rc = launch_accumulate(e, p, t_begin);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return CITAM_OK;
+}
+
+// One chunk of the split pipeline (citam_run without the contact log): agents that stand still from
+// the halo step to the chunk's end are binned ONCE (fine grid); the others -- walking, arriving,
+// leaving, or changing segment inside the chunk -- are expanded, binned (coarse grid) and sorted per
+// step.  Only a range's first step looks at static-static pairs (k_pairs on the static array): at every
+// other step such a pair is inside a run that an earlier step added in one piece.
+static int run_split_chunk(citam_engine* e, int tb, int steps) {
+  Params p = make_params(e);
+  p.chunk_begin = tb;
+  const int rows = steps + 1;  // + halo row for step tb-1
+  CK(cudaMemsetAsync(e->scells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
+  CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->dcells_stride * steps, e->stream));
+  CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
+  CK(cudaMemsetAsync(e->dyn_count, 0, sizeof(uint32_t), e->stream));
+  const int gN = (e->N + 255) / 256;
+  const int wide = 148 * 8;  // grid-stride kernels over the (device-side) dynamic count
+  {
+    Timed tm(e, CITAM_K_EXPAND_BIN);
+    k_classify<<<gN, 256, 0, e->stream>>>(p, tb, steps);
+    e->launches++;
+    k_expand_dyn<<<wide * 2, 128, 0, e->stream>>>(p, tb - 1, rows, 16);
+  }
+  launch_scan(e, e->scells, e->cells_stride, e->total_cells + 1, 1);
+  launch_scan(e, e->cells, e->dcells_stride, e->dtotal_cells + 1, steps);
+  const bool first = tb == e->range_begin;
+  {
+    Timed tm(e, CITAM_K_SCATTER);
+    k_scatter_static<<<gN, 256, 0, e->stream>>>(p);
+    k_scatter_dyn<<<wide, 256, 0, e->stream>>>(p, steps, tb);
+    k_select_changed_dyn<<<dim3(16, steps), 256, 0, e->stream>>>(p, steps, first ? 0 : -1);
+    e->launches += 2;
+  }
+  {
+    Timed tm(e, CITAM_K_PAIRS);
+    if (first) {
+      k_pairs<<<dim3(gN, 1), 256, 0, e->stream>>>(p, tb, 1, 1, 1);
       e->launches++;
     }
-    CK(cudaEventRecord(e->ev_applied[e->cur], e->stream2));
-    e->applied_pending[e->cur] = true;
+    k_pairs_changed_split<<<dim3(64, steps), kPC, 0, e->stream>>>(p, tb, steps, first ? 0 : -1);
   }
+  int rc = launch_accumulate(e, p, tb);
+  if (rc) return rc;
   CK(cudaGetLastError());
   return CITAM_OK;
 }
@@ -1738,6 +2186,8 @@ static int maybe_grow_pairs(citam_engine* e, bool now) {
 
 static int create_impl(citam_engine* e, const citam_config* cfg) {
   if (const char* g = getenv("CITAM_ACC_BLOCKS")) e->acc_blocks = std::max(1, atoi(g));
+  if (const char* g = getenv("CITAM_NO_SPLIT")) e->no_split = atoi(g) != 0;
+  if (const char* g = getenv("CITAM_NO_FAST_STATS")) e->no_fast_stats = atoi(g) != 0;
   e->cfg = *cfg;
   e->device = cfg->device;
   e->N = cfg->n_agents;
@@ -1854,7 +2304,7 @@ void citam_destroy(citam_engine* e) {
   for (auto p : e->adj_d) cudaFree(p);
   cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->window_d); cudaFree(e->pairs);
   cudaFree(e->coords); cudaFree(e->hist);
-  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->ctr_d);
+  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->dur_out); cudaFree(e->ctr_d);
   cudaFree(e->flag_d); cudaFree(e->prev); cudaFree(e->states_d);
   cudaGetLastError();
   delete e;
@@ -1880,6 +2330,8 @@ int citam_reset(citam_engine* e) {
   e->prev_step = LLONG_MIN;
   e->agent_steps = 0;
   e->max_step = 0;
+  e->counters_match = true;
+  e->steps_since_reset = 0;
   return CITAM_OK;
 }
 
@@ -1892,6 +2344,7 @@ int citam_clear_pairs(citam_engine* e) {
   CK(cudaMemsetAsync(&e->ctr_d->pair_used, 0, sizeof(unsigned long long), e->stream));
   CK(cudaMemsetAsync(e->ctr_d->pair_used_sub, 0, sizeof(unsigned long long) * kSubBuffers * kCounterStride, e->stream));
   e->snap_pending = false;
+  e->counters_match = false;
   return CITAM_OK;
 }
 
@@ -2030,6 +2483,9 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
   if (!e->have_itin) return fail(CITAM_ERR_STATE, "citam_run before citam_load_itineraries");
   if (t_begin < 0 || t_end < t_begin || t_end > (1 << 24) - 1) return fail(CITAM_ERR_INVALID, "bad step range (steps < 2^24 - 1)");
   if (t_end == t_begin) return CITAM_OK;
+  if ((double)(e->N - 1) * (double)(e->steps_since_reset + (unsigned long long)(t_end - t_begin)) >= 1099511627776.0)
+    return fail(CITAM_ERR_CAPACITY, "(n_agents - 1) x steps since the last reset must stay below 2^40 (per-agent counter width)");
+  e->steps_since_reset += (unsigned long long)(t_end - t_begin);
   CK(cudaSetDevice(e->device));
   int rc = ensure_ready(e, 1);  // uploads floor descriptors so pick_chunk sees the grid
   if (rc) return rc;
@@ -2047,6 +2503,8 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     e->window_dirty = false;
   }
   e->max_step = std::max<uint32_t>(e->max_step, (uint32_t)t_end);
+  // static / dynamic split of the agents per chunk: whenever runs are aggregated (no contact log)
+  struct Split { bool& f; Split(bool& x, bool v) : f(x) { f = v; } ~Split() { f = false; } } split_scope(e->split, e->log_cap == 0 && !e->no_split);
   // a contact run is one table update however many chunks it crosses; runs are clipped to the range
   // (and to 2^20 steps, the width of the run field: longer ranges are processed as several)
   for (int rb = t_begin; rb < t_end; rb += (1 << kMaxRunLog2)) {
@@ -2055,8 +2513,16 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
     for (int tb = rb; tb < e->range_end; tb += S) {
       rc = begin_chunk(e);
       if (rc) return rc;
-      Params p = make_params(e);
       int steps = std::min(S, e->range_end - tb);
+      if (e->split) {
+        rc = run_split_chunk(e, tb, steps);
+        if (rc) return rc;
+        e->agent_steps += (unsigned long long)steps * e->N;
+        rc = maybe_grow_pairs(e, false);
+        if (rc) return rc;
+        continue;
+      }
+      Params p = make_params(e);
       int rows = steps + 1;  // + halo row for step tb-1
       CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->cells_stride * steps, e->stream));
       CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
@@ -2086,6 +2552,9 @@ int citam_run(citam_engine* e, int32_t t_begin, int32_t t_end) {
 int citam_step_states(citam_engine* e, int32_t step, const citam_agent_state* states) {
   if (!e || !states) return fail(CITAM_ERR_INVALID, "null argument");
   if (step < 0 || step > (1 << 24) - 2) return fail(CITAM_ERR_INVALID, "step out of range");
+  if ((double)(e->N - 1) * (double)(e->steps_since_reset + 1) >= 1099511627776.0)
+    return fail(CITAM_ERR_CAPACITY, "(n_agents - 1) x steps since the last reset must stay below 2^40 (per-agent counter width)");
+  e->steps_since_reset += 1;
   CK(cudaSetDevice(e->device));
   int rc = ensure_ready(e, 1);
   if (rc) return rc;
@@ -2392,7 +2861,13 @@ int citam_export_agent_durations(citam_engine* e, uint64_t* out) {
   CK(cudaSetDevice(e->device));
   int rc = check_overflow(e);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out, e->agent_dur, sizeof(uint64_t) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+  if (!e->dur_out) CK(cudaMalloc(&e->dur_out, sizeof(unsigned long long) * (size_t)e->N));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_unpack_durations<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->agent_dur, e->N, e->dur_out);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->dur_out, sizeof(uint64_t) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return CITAM_OK;
 }
@@ -2488,8 +2963,43 @@ int citam_statistics_end(citam_engine* e, citam_stats* out) {
   return CITAM_OK;
 }
 
+// Statistics from the per-agent counter words and the table's pair count alone: O(n_agents).  Valid
+// when the words describe the pairs of the run -- this engine's own (nothing merged or cleared), or
+// the whole run's after the all-reduce of citam_agent_durations_device (n_pairs is then this engine's
+// share: add it over the ranks).  CITAM_ERR_CAPACITY when some agent has >= 2^24 contact-steps (its
+// event field may have wrapped): use the table pass (citam_statistics_begin/_end) then.
+int citam_statistics_counters(citam_engine* e, citam_stats* out) {
+  if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  int rc = check_overflow(e);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(e->ctr_d->stats, 0, sizeof(unsigned long long) * 6, e->stream));
+  {
+    Timed tm(e, CITAM_K_FINALIZE);
+    k_stats_counters<<<(e->N + 255) / 256, 256, 0, e->stream>>>(e->agent_dur, e->agent_nev, e->agent_has, e->N, e->ctr_d);
+  }
+  CK(cudaGetLastError());
+  DevCounters c;
+  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (c.stats[5] >= (1ULL << (64 - kAgentDurBits)))
+    return fail(CITAM_ERR_CAPACITY, "an agent has %llu contact-steps: its event count needs the pass over the pair table", c.stats[5]);
+  out->total_duration = c.stats[0] / 2;
+  out->n_pairs = pairs_used(c);
+  out->n_agents_with_contacts = c.stats[2];
+  out->sum_events_per_agent = c.stats[3];
+  out->max_events_per_agent = c.stats[4];
+  out->reserved = 0;
+  return CITAM_OK;
+}
+
 int citam_statistics(citam_engine* e, citam_stats* out) {
   if (!e || !out) return fail(CITAM_ERR_INVALID, "null argument");
+  if (e->counters_match && !e->no_fast_stats) {
+    int rc = citam_statistics_counters(e, out);
+    if (rc != CITAM_ERR_CAPACITY) return rc;
+    rc = check_overflow(e);  // a table overflow is final; a wide agent counter is not
+    if (rc) return rc;
+  }
   int rc = citam_statistics_begin(e);
   if (rc) return rc;
   return citam_statistics_end(e, out);
@@ -2507,6 +3017,7 @@ int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elemen
   if (!e || !ptr || !n_elements) return fail(CITAM_ERR_INVALID, "null argument");
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  e->counters_match = false;  // the caller is about to reduce other ranks' words into the array
   *ptr = e->agent_dur;
   *n_elements = (uint64_t)e->N;
   return CITAM_OK;
@@ -2584,6 +3095,7 @@ int citam_merge_pairs_device(citam_engine* e, const citam_pair* pairs_device, ui
   Params p = make_params(e);
   {
     Timed tm(e, CITAM_K_FINALIZE);
+    e->counters_match = false;
     k_merge_pairs<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, pairs_device, n, e->flag_d);
   }
   CK(cudaGetLastError());

@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import COORD, PAIR
+from ._lib import COORD, PAIR, CitamCapacityError
 
 
 def plan_blocks(total_timesteps: int, block: int, world: int, rank: int) -> List[Tuple[int, int]]:
@@ -243,6 +243,21 @@ class ShardedRun:
 
         dist = _dist()
         eng = self.engine
+        # after `reduce` the per-agent counter words are the whole run's (seconds | events << 40): the
+        # sums need no pass over the pair table; n_pairs is this rank's share
+        fast = None
+        if self.info:
+            try:
+                fast = eng.statistics_counters()
+            except CitamCapacityError:
+                fast = None
+        ok = torch.tensor([1 if fast is not None else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()):
+            t = torch.tensor([fast["n_pairs"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            fast["n_pairs"] = int(t.item())
+            return fast
         eng.statistics_begin()
         a, b, n = eng.stats_arrays_device()
         dist.all_reduce(device_tensor(a, n, "<i4"))

@@ -220,7 +220,8 @@ class DeviceEngine:
 
     # -- device-resident results (multi-GPU exchange, large runs) ------------------------------
     def agent_durations_device(self):
-        """(device pointer, n) of the live uint64 per-agent contact seconds, for the NCCL all-reduce."""
+        """(device pointer, n) of the live uint64 per-agent counter words (contact seconds in bits 0-39,
+        contact events above), for the NCCL all-reduce; `agent_durations()` returns the seconds."""
         p = C.c_void_p()
         n = C.c_uint64()
         L.check(self.lib.citam_agent_durations_device(self._h, C.byref(p), C.byref(n)))
@@ -272,6 +273,13 @@ class DeviceEngine:
 
     def statistics_begin(self) -> None:
         L.check(self.lib.citam_statistics_begin(self._h))
+
+    def statistics_counters(self) -> Dict[str, int]:
+        """Statistics sums from the per-agent counter words + the table's pair count (O(n_agents));
+        raises CitamDeviceError(ERR_CAPACITY) when an agent's event field is not provably exact."""
+        s = L.Stats()
+        L.check(self.lib.citam_statistics_counters(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in L.Stats._fields_ if k != "reserved"}
 
     def statistics_end(self) -> Dict[str, int]:
         s = L.Stats()

@@ -23,7 +23,9 @@
  *   floors <= 63, spaces per floor <= 32767, location-table sides <= 65536,
  *   steps < 2^24 - 1, |coordinates| < 2^26, per-step stride of a segment within
  *   int16, contact-steps per pair < 2^24 and events per pair < 2^16,
- *   steps_per_chunk <= 1024, fewer than 2^32 records per export.  Itinerary
+ *   (n_agents - 1) x steps run since the last reset < 2^40 (the most contact-
+ *   steps one agent can collect), steps_per_chunk <= 1024, fewer than 2^32
+ *   records per export.  Itinerary
  *   coordinates are integers (the reference's navigation lattice); contact
  *   positions are their midpoints, reported as (x1+x2, y1+y2).
  *   citam_load_itineraries checks the segment store on the device: seg_off
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CITAM_ABI_VERSION 2
+#define CITAM_ABI_VERSION 3
 
 typedef enum {
   CITAM_OK = 0,
@@ -245,7 +247,9 @@ int citam_get_timings(citam_engine* e, citam_timings* out);
  *                                citam_stats_arrays_device arrays, citam_statistics_end
  *                                (total_duration and n_pairs are then per-share sums:
  *                                add them over the ranks)
- * Device views are the live arrays: uint64 [n_agents] contact seconds, uint64
+ * Device views are the live arrays: uint64 [n_agents] per-agent counter words
+ * (contact seconds in bits 0-39, contact events in bits 40-63; sums of words are
+ * sums of both fields; citam_export_agent_durations returns the seconds), uint64
  * [n] histogram buckets (NULL/0 when the hashed histogram is in use), uint32
  * [n_agents] events per agent and has-contact flags. */
 int citam_agent_durations_device(citam_engine* e, void** ptr, uint64_t* n_elements);
@@ -265,6 +269,13 @@ int citam_clear_pairs(citam_engine* e); /* empty the pair table only */
 int citam_merge_pairs_device(citam_engine* e, const citam_pair* pairs_device, uint64_t n);
 int citam_merge_pairs(citam_engine* e, const citam_pair* pairs, uint64_t n);
 int citam_merge_coords(citam_engine* e, const citam_coord* coords, uint64_t n);
+/* Statistics from the per-agent counter words and the pair count alone, O(n_agents), no
+ * pass over the pair table: valid when the words describe the run's pairs -- this engine's
+ * own (citam_statistics takes this path by itself), or the whole run's after the all-reduce
+ * of citam_agent_durations_device (n_pairs is then this engine's share: add it over the
+ * ranks).  CITAM_ERR_CAPACITY if an agent has >= 2^24 contact-steps (its event count is then
+ * not provably exact): use citam_statistics_begin/_end. */
+int citam_statistics_counters(citam_engine* e, citam_stats* out);
 int citam_statistics_begin(citam_engine* e);
 int citam_stats_arrays_device(citam_engine* e, void** events_per_agent, void** has_contact,
                               uint64_t* n_elements);

@@ -46,9 +46,12 @@ def test_device_lut_equals_rectangle_rule(synth):
     eng.close()
 
 
-@pytest.mark.parametrize("chunk", [0, 37])
-def test_tables_bit_exact_vs_grid_oracle(synth, chunk):
+@pytest.mark.parametrize("chunk,no_split", [(0, 0), (37, 0), (5, 0), (37, 1)])
+def test_tables_bit_exact_vs_grid_oracle(synth, chunk, no_split, monkeypatch):
+    """Both step pipelines: the static/dynamic split (default without a contact log) and the one that
+    expands and bins every agent at every step (CITAM_NO_SPLIT=1)."""
     fac, seg_off, segs, p, T, want, want_contacts = synth
+    monkeypatch.setenv("CITAM_NO_SPLIT", str(no_split))
     eng = _engine(fac, seg_off, segs, p, steps_per_chunk=chunk)
     eng.run(0, T)
     got = tables_of(eng)
@@ -56,6 +59,34 @@ def test_tables_bit_exact_vs_grid_oracle(synth, chunk):
     assert got[2] == want[2]
     assert got[0] == want[0]
     assert got[1] == want[1]
+    eng.close()
+
+
+def test_statistics_from_counter_words_equal_the_table_pass(synth, monkeypatch):
+    """citam_statistics' O(n_agents) path (per-agent words: seconds | events << 40) against the pass
+    over the pair table, and both against sums taken from the oracle's pair rows."""
+    fac, seg_off, segs, p, T, want, _ = synth
+    eng = _engine(fac, seg_off, segs, p)
+    eng.run(0, T)
+    fast = eng.statistics_sums()
+    assert fast == eng.statistics_counters()
+    eng.statistics_begin()
+    slow = eng.statistics_end()
+    assert fast == slow
+    nev = {}
+    for a1, a2, _first, n_events, _dur in want[0]:
+        nev[a1] = nev.get(a1, 0) + n_events
+        nev[a2] = nev.get(a2, 0) + n_events
+    assert fast["n_pairs"] == len(want[0])
+    assert fast["total_duration"] == sum(r[4] for r in want[0])
+    assert fast["n_agents_with_contacts"] == len(nev)
+    assert fast["sum_events_per_agent"] == sum(nev.values())
+    assert fast["max_events_per_agent"] == (max(nev.values()) if nev else 0)
+    eng.close()
+    monkeypatch.setenv("CITAM_NO_FAST_STATS", "1")
+    eng = _engine(fac, seg_off, segs, p)
+    eng.run(0, T)
+    assert eng.statistics_sums() == fast
     eng.close()
 
 

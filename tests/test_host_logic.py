@@ -69,7 +69,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.citam_abi_version() == L.ABI_VERSION == 2
+    assert lib.citam_abi_version() == L.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback_without_device():
