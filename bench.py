@@ -332,10 +332,12 @@ def default_pair_cap(args, p, world):
     N = p["n_agents"]
     if args.mode == "blocks":
         return int(min(1 << 31, max(1 << 22, 2048 * N)))
-    # whole day: ~1 700 distinct partners per agent and day on these crowded floors (measured, config 3);
+    # whole day: ~250 distinct pairs per agent and day on these crowded floors (measured, config 3: 2.5e8 pairs);
     # a rank's table holds its own range's pairs before the exchange and its share of all pairs after it
-    est = {"config5": 4096}.get(args.workload, 2048) * N
-    per_rank = est if world == 1 else max(est // world * 2, est // 2)
+    # (pairs that meet in several ranks' ranges are held by each of them: twice the even share is allowed
+    # for).  The table is at most half full at these sizes; a table that overflows aborts the bench.
+    est = {"config5": 4096}.get(args.workload, 320) * N
+    per_rank = est if world == 1 else 2 * est // world
     cap = 1 << 22
     while cap < 2 * per_rank:
         cap <<= 1

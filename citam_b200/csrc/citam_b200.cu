@@ -125,7 +125,8 @@ struct DevCounters {
   unsigned long long export_cursor;
   unsigned long long stats[6];
   unsigned long long contact_runs;
-  unsigned long long pad[2];
+  unsigned long long merged_max_step;  // largest first-contact step of a merged record
+  unsigned long long pad[1];
   unsigned long long cbuf_count[2][kSubBuffers * kCounterStride];  // one set per contact buffer
   unsigned long long pair_used_sub[kSubBuffers * kCounterStride];  // spread: inserts are frequent
 };
@@ -178,6 +179,7 @@ struct Params {
   uint32_t* scells;         // [cells_stride] static cell counts -> starts
   uint32_t* dyn_agent;      // [N] agent of dynamic index j
   uint32_t* dyn_count;      // dynamic agents of this chunk
+  uint32_t* seg_cur;        // [N] per agent: 1 + index (inside its segments) of the segment k_classify last found
   DevCounters* ctr;
 };
 constexpr uint32_t kClsOut = 0xFFFFFFFFu, kClsStatic = 0xFFFFFFFEu;
@@ -293,8 +295,14 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
   int2 win = make_int2(INT_MIN, INT_MAX);
   if (do_bin && p.window != nullptr) {
     win = p.window[a];
-    // nothing of this thread's steps lies in [enter - 1, exit): no record is written (none is read)
-    if (win.x > t_first + min(r0 + kRowsPerThread, rows) || win.y <= t_first + r0) return;
+    // nothing of this thread's steps lies in [enter - 1, exit): no record is written (none is read);
+    // the split pipeline's rows say "not around" instead, so that its scatter needs no window
+    if (win.x > t_first + min(r0 + kRowsPerThread, rows) || win.y <= t_first + r0) {
+      if (coarse)
+        for (int row = r0; row < min(r0 + kRowsPerThread, rows); ++row)
+          p.rec[(size_t)row * p.N + slot] = make_int4(0, 0, pack_fl(-1, -1), 0);
+      return;
+    }
   }
   long long sb = p.seg_off[a], se = p.seg_off[a + 1];
   int t = t_first + r0;
@@ -311,43 +319,59 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
   if (c + 1 < se) next_t0 = __ldg(&p.segs[c + 1].x) & 0xffffff;
   int lastx = INT_MIN, lasty = INT_MIN, lastf = -1, loc = -1;
   const int stride = coarse ? p.dcells_stride : p.cells_stride;
+  // rows in groups of kGroup: the group's records are computed first, then its rank atomics are issued
+  // together and its stores follow -- a thread waits once per group for an atomic's round trip, not
+  // once per row (the kernel is bound by that latency)
+  constexpr int kGroup = 4;
+  const int row_end = min(r0 + kRowsPerThread, rows);
 #pragma unroll 1
-  for (int r = 0; r < kRowsPerThread; ++r) {
-    int row = r0 + r;
-    if (row >= rows) break;
-    t = t_first + row;
-    while (t >= next_t0) {
-      ++c;
-      s = __ldg(&p.segs[c]);
-      next_t0 = (c + 1 < se) ? (__ldg(&p.segs[c + 1].x) & 0xffffff) : INT_MAX;
+  for (int rg = r0; rg < row_end; rg += kGroup) {
+    int4 out[kGroup];
+    int cellv[kGroup];  // >= 0: cell to take a rank in; -1: store as is; -2: no store
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+      const int row = rg + k;
+      cellv[k] = -2;
+      if (row >= row_end) continue;
+      t = t_first + row;
+      while (t >= next_t0) {
+        ++c;
+        s = __ldg(&p.segs[c]);
+        next_t0 = (c + 1 < se) ? (__ldg(&p.segs[c + 1].x) & 0xffffff) : INT_MAX;
+      }
+      out[k] = make_int4(0, 0, pack_fl(-1, -1), 0);
+      if (t + 1 < win.x || t >= win.y) {  // outside the agent's window (see k_agent_windows)
+        if (coarse) cellv[k] = -1;
+        continue;
+      }
+      cellv[k] = -1;
+      if (c < sb || t < 0) continue;
+      const int dt = t - (s.x & 0xffffff);
+      const int f = (s.x >> 24) & 0xff;
+      const int x = s.y + (int)(int16_t)(s.w & 0xffff) * dt;
+      const int y = s.z + (int)(int16_t)((uint32_t)s.w >> 16) * dt;
+      if (x != lastx || y != lasty || f != lastf) {
+        loc = (f < p.F) ? lut_lookup(p.floors[f], x, y) : -1;
+        lastx = x; lasty = y; lastf = f;
+      }
+      // stationary inside one segment: same state as the step before, and until the next segment starts
+      const bool still = s.w == 0;
+      const int changed = !(still && dt >= 1);
+      if (loc < 0) {  // in the facility, in no space: never binned, never in contact
+        out[k] = make_int4(x, y, pack_fl(f, -1, changed, still ? 0 : 1), 0);
+        continue;
+      }
+      const FloorDev& fd = p.floors[f];
+      const int32_t xy = (x - fd.minx) | ((y - fd.miny) << 16);
+      out[k] = make_int4(xy, still ? next_t0 : t + 1, pack_fl(f, loc, changed, still ? 0 : 1), 0);
+      if (do_bin && row >= 1) cellv[k] = coarse ? dcell_of_xy(p, fd, xy) : cell_of_xy(p, fd, xy);
     }
-    size_t o = (size_t)row * p.N + slot;
-    if (t + 1 < win.x || t >= win.y) continue;  // outside the agent's window (see k_agent_windows)
-    if (c < sb || t < 0) {
-      p.rec[o] = make_int4(0, 0, pack_fl(-1, -1), 0);
-      continue;
-    }
-    int dt = t - (s.x & 0xffffff);
-    int f = (s.x >> 24) & 0xff;
-    int x = s.y + (int)(int16_t)(s.w & 0xffff) * dt;
-    int y = s.z + (int)(int16_t)((uint32_t)s.w >> 16) * dt;
-    if (x != lastx || y != lasty || f != lastf) {
-      loc = (f < p.F) ? lut_lookup(p.floors[f], x, y) : -1;
-      lastx = x; lasty = y; lastf = f;
-    }
-    // stationary inside one segment: same state as the step before, and until the next segment starts
-    const bool still = s.w == 0;
-    const int changed = !(still && dt >= 1);
-    if (loc < 0) {  // in the facility, in no space: never binned, never in contact
-      p.rec[o] = make_int4(x, y, pack_fl(f, -1, changed, still ? 0 : 1), 0);
-      continue;
-    }
-    const FloorDev& fd = p.floors[f];
-    const int32_t xy = (x - fd.minx) | ((y - fd.miny) << 16);
-    uint32_t rk = 0;
-    if (do_bin && row >= 1)
-      rk = atomicAdd(&p.cells[(size_t)(row - 1) * stride + (coarse ? dcell_of_xy(p, fd, xy) : cell_of_xy(p, fd, xy))], 1u);
-    p.rec[o] = make_int4(xy, still ? next_t0 : t + 1, pack_fl(f, loc, changed, still ? 0 : 1), (int)rk);
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k)
+      if (cellv[k] >= 0) out[k].w = (int)atomicAdd(&p.cells[(size_t)(rg + k - 1) * stride + cellv[k]], 1u);
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k)
+      if (cellv[k] != -2) p.rec[(size_t)(rg + k) * p.N + slot] = out[k];
   }
 }
 
@@ -372,17 +396,41 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
     if (!(win.x > tb + S || win.y <= tb - 1)) {
       const int t = tb - 1;
       const long long sb = p.seg_off[a], se = p.seg_off[a + 1];
-      long long lo = sb, hi = se;  // first segment with t0 > t
-      while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        int t0 = __ldg(&p.segs[mid].x) & 0xffffff;
-        if (t0 <= t) lo = mid + 1; else hi = mid;
+      // the segment holding step t: chunks mostly follow one another in time, so the segment found for
+      // the previous chunk (seg_cur: its index + 1, 0 = before the first) or one of the next few is
+      // nearly always the one; otherwise a binary search
+      long long lo = sb + (long long)p.seg_cur[a];  // candidate for "first segment with t0 > t"
+      int4 s = make_int4(0, 0, 0, 0);
+      int next_t0 = INT_MAX;
+      bool found = false;
+      if (lo <= se) {
+        bool below = true;
+        if (lo > sb) { s = __ldg(&p.segs[lo - 1]); below = (s.x & 0xffffff) <= t; }
+        if (below) {
+          for (int k = 0; k < 4; ++k) {
+            if (lo >= se) { next_t0 = INT_MAX; found = true; break; }
+            const int4 nx = __ldg(&p.segs[lo]);
+            if ((nx.x & 0xffffff) > t) { next_t0 = nx.x & 0xffffff; found = true; break; }
+            s = nx;
+            ++lo;
+          }
+        }
       }
+      if (!found) {
+        long long hi = se;
+        lo = sb;
+        while (lo < hi) {
+          long long mid = (lo + hi) >> 1;
+          int t0 = __ldg(&p.segs[mid].x) & 0xffffff;
+          if (t0 <= t) lo = mid + 1; else hi = mid;
+        }
+        if (lo > sb) s = __ldg(&p.segs[lo - 1]);
+        next_t0 = (lo < se) ? (__ldg(&p.segs[lo].x) & 0xffffff) : INT_MAX;
+      }
+      p.seg_cur[a] = (uint32_t)(lo - sb);
       const long long ci = lo - 1;
       dyn = true;
       if (ci >= sb && t >= 0) {
-        const int4 s = __ldg(&p.segs[ci]);
-        const int next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
         if (s.w == 0 && next_t0 >= tb + S) {
           dyn = false;
           const int f = (s.x >> 24) & 0xff;
@@ -431,19 +479,18 @@ __global__ void __launch_bounds__(128) k_expand_dyn(Params p, int t_first, int r
   }
 }
 
-__global__ void __launch_bounds__(256) k_scatter_dyn(Params p, int rows /* S */, int t_begin) {
+__global__ void __launch_bounds__(256) k_scatter_dyn(Params p, int rows /* S */) {
   const uint32_t Dn = *p.dyn_count;
-  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < (unsigned long long)Dn * rows;
-       w += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint32_t row = (uint32_t)(w / Dn), j = (uint32_t)(w - (unsigned long long)row * Dn);
-    const uint32_t a = p.dyn_agent[j];
-    const int2 win = p.window[a];
-    const int t = t_begin + (int)row;
-    if (t < win.x || t >= win.y) continue;  // no record was written
-    const int4 r = p.rec[(size_t)(row + 1) * p.N + j];
+  const int row = blockIdx.y;
+  if (row >= rows) return;
+  const int4* rec = p.rec + (size_t)(row + 1) * p.N;
+  const uint32_t* cs = p.cells + (size_t)row * p.dcells_stride;
+  int4* out = p.sorted + (size_t)row * p.N;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < Dn; j += gridDim.x * blockDim.x) {
+    const int4 r = rec[j];  // every row of a dynamic agent is written ("not around" outside its window)
     if (!fl_located(r.z)) continue;
-    const uint32_t dest = p.cells[(size_t)row * p.dcells_stride + dcell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
-    p.sorted[(size_t)row * p.N + dest] = make_int4(r.x, (int)a, r.z, r.y);
+    const uint32_t dest = cs[dcell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
+    out[dest] = make_int4(r.x, (int)p.dyn_agent[j], r.z, r.y);
   }
 }
 
@@ -689,6 +736,23 @@ __device__ __forceinline__ unsigned long long pair_slot(const Params& p, unsigne
   unsigned long long h = mix64(key) & p.pair_mask;
   for (int probe = 0; probe < kMaxProbes; ++probe) {
     ulonglong2 e = load_entry(&p.pairs[h]);
+    if (e.x == key) { *acc_seen = e.y; return h; }
+    if (e.x == 0ULL) {
+      unsigned long long old = atomicCAS(&p.pairs[h].key, 0ULL, key);
+      if (old == 0ULL) { count_insert(p); *acc_seen = 0ULL; return h; }
+      if (old == key) { *acc_seen = *(volatile unsigned long long*)&p.pairs[h].acc; return h; }
+    }
+    h = (h + 1) & p.pair_mask;
+  }
+  atomicOr(&p.ctr->overflow, OVF_PAIR);
+  return ~0ULL;
+}
+
+// The same when the caller has already fetched the entry at the key's home slot `h`.
+__device__ __forceinline__ unsigned long long pair_slot_from(const Params& p, unsigned long long key, unsigned long long h,
+                                                             ulonglong2 e, unsigned long long* acc_seen) {
+  for (int probe = 0; probe < kMaxProbes; ++probe) {
+    if (probe) e = load_entry(&p.pairs[h]);
     if (e.x == key) { *acc_seen = e.y; return h; }
     if (e.x == 0ULL) {
       unsigned long long old = atomicCAS(&p.pairs[h].key, 0ULL, key);
@@ -1093,17 +1157,23 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
 // The same for the split pipeline: the changed agents of a step are all dynamic; each is tested
 // against the chunk's STATIC agents (3 x 3 fine cells of `scells` / `ssorted`: three ranges) and
 // against the step's DYNAMIC agents (3 x 3 coarse cells of the step's row of `cells` / `sorted`:
-// three more ranges) -- six contiguous ranges per agent, flattened over the batch as above.  A
-// static agent never owns a pair with a changed one; two dynamic agents: the lower id owns the
-// pair if the other one is changed too (on `all_row`, the first step of a range, every dynamic
-// agent counts as changed: that step owns every contact it finds, static-static pairs are k_pairs').
+// three more ranges) -- six contiguous ranges per agent.  The batch's candidates are flattened into
+// one index space; a shared-memory tile maps a flat index to its (agent, range) -- filled by the
+// agents' threads, read back with one load per candidate (the binary search this replaces was a
+// quarter of the kernel's instructions) -- and `s_delta` turns the flat index into the candidate's
+// position in the sorted array.  A static agent never owns a pair with a changed one; two dynamic
+// agents: the lower id owns the pair if the other one is changed too (on `all_row`, the first step of
+// a range, every dynamic agent counts as changed: that step owns every contact it finds,
+// static-static pairs are k_pairs').
+constexpr int kTile = 4096;  // candidates per tile of the flat index space
+
 __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_begin, int rows /* S */, int all_row) {
   __shared__ ContactRec hitbuf[kPC * kHitSlots];
   __shared__ int4 s_me[kPC];
-  __shared__ int s_qs[6][kPC];
-  __shared__ int s_cum[5][kPC];  // ends of ranges 0..4 in the agent's candidate index space
-  __shared__ int s_off[kPC + 1];
+  __shared__ int s_delta[kPC * 6];        // candidate position = flat index + s_delta[agent * 6 + range]
+  __shared__ uint16_t s_owner[kTile];     // agent * 6 + range of a flat index (relative to the tile)
   __shared__ int s_warp[kPC / 32];
+  __shared__ int s_total;
   __shared__ int s_void;
   const int row = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1123,24 +1193,25 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
   ContactRec* mine = hitbuf + threadIdx.x * kHitSlots;
   unsigned long long tests = 0, hits = 0, runs = 0;
   for (uint32_t base = blockIdx.x * kPC; base < n; base += gridDim.x * kPC) {
-    // ---- phase 1: one thread per agent describes its candidate ranges
+    // ---- phase 1: one thread per agent describes its six candidate ranges
     const uint32_t idx = base + threadIdx.x;
     int total = 0;
+    int qs[6], len[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { qs[r] = 0; len[r] = 0; }
     if (idx < n) {
       const int4 me = srt[p.chg_list[(size_t)row * p.N + idx]];
       const FloorDev& fd = p.floors[fl_floor(me.z)];
-      int len[6];
       {
         const int cx = div_cell(p, xy_x(me.x)), cy = div_cell(p, xy_y(me.x));
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, fd.ncx - 1);
         const int rb = fd.cell_base + cy * fd.ncx;
         const bool up = cy + 1 < fd.ncy, dn = cy > 0;
         const int rbu = up ? rb + fd.ncx : rb, rbd = dn ? rb - fd.ncx : rb;
-        const int q0 = (int)cs[rbd + x0], q1 = (int)cs[rb + x0], q2 = (int)cs[rbu + x0];
-        len[0] = dn ? (int)cs[rbd + x1 + 1] - q0 : 0;
-        len[1] = (int)cs[rb + x1 + 1] - q1;
-        len[2] = up ? (int)cs[rbu + x1 + 1] - q2 : 0;
-        s_qs[0][threadIdx.x] = q0; s_qs[1][threadIdx.x] = q1; s_qs[2][threadIdx.x] = q2;
+        qs[0] = (int)cs[rbd + x0]; qs[1] = (int)cs[rb + x0]; qs[2] = (int)cs[rbu + x0];
+        len[0] = dn ? (int)cs[rbd + x1 + 1] - qs[0] : 0;
+        len[1] = (int)cs[rb + x1 + 1] - qs[1];
+        len[2] = up ? (int)cs[rbu + x1 + 1] - qs[2] : 0;
       }
       {
         const int cx = div_dcell(p, xy_x(me.x)), cy = div_dcell(p, xy_y(me.x));
@@ -1148,16 +1219,14 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
         const int rb = fd.dcell_base + cy * fd.dncx;
         const bool up = cy + 1 < fd.dncy, dn = cy > 0;
         const int rbu = up ? rb + fd.dncx : rb, rbd = dn ? rb - fd.dncx : rb;
-        const int q0 = (int)cd[rbd + x0], q1 = (int)cd[rb + x0], q2 = (int)cd[rbu + x0];
-        len[3] = dn ? (int)cd[rbd + x1 + 1] - q0 : 0;
-        len[4] = (int)cd[rb + x1 + 1] - q1;
-        len[5] = up ? (int)cd[rbu + x1 + 1] - q2 : 0;
-        s_qs[3][threadIdx.x] = q0; s_qs[4][threadIdx.x] = q1; s_qs[5][threadIdx.x] = q2;
+        qs[3] = (int)cd[rbd + x0]; qs[4] = (int)cd[rb + x0]; qs[5] = (int)cd[rbu + x0];
+        len[3] = dn ? (int)cd[rbd + x1 + 1] - qs[3] : 0;
+        len[4] = (int)cd[rb + x1 + 1] - qs[4];
+        len[5] = up ? (int)cd[rbu + x1 + 1] - qs[5] : 0;
       }
       s_me[threadIdx.x] = me;
 #pragma unroll
-      for (int r = 0; r < 5; ++r) { total += len[r]; s_cum[r][threadIdx.x] = total; }
-      total += len[5];
+      for (int r = 0; r < 6; ++r) total += len[r];
     }
     // block exclusive scan of the candidate counts
     int inc = total;
@@ -1169,53 +1238,62 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
     __syncthreads();
     int woff = 0;
     for (int w = 0; w < wid; ++w) woff += s_warp[w];
-    s_off[threadIdx.x] = woff + inc - total;
-    if (threadIdx.x == kPC - 1) s_off[kPC] = woff + inc;
+    int start[6];  // first flat index of each range
+    {
+      int o = woff + inc - total;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        start[r] = o;
+        s_delta[threadIdx.x * 6 + r] = qs[r] - o;
+        o += len[r];
+      }
+    }
+    if (threadIdx.x == kPC - 1) s_total = woff + inc;
     __syncthreads();
-    const int P = s_off[kPC];
-    // ---- phase 2: one candidate test per thread and iteration
+    const int P = s_total;
     int nh = 0;
-    for (int pp = threadIdx.x; pp < P; pp += kPC) {
-      int lo = 0, hi = kPC;  // largest i with s_off[i] <= pp
+    for (int tile = 0; tile < P; tile += kTile) {
+      // ---- the tile's flat index -> (agent, range) map
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        int mid = (lo + hi) >> 1;
-        if (s_off[mid] <= pp) lo = mid; else hi = mid;
+      for (int r = 0; r < 6; ++r) {
+        const int lo = max(start[r], tile) - tile, hi = min(start[r] + len[r], tile + kTile) - tile;
+        const uint16_t o = (uint16_t)(threadIdx.x * 6 + r);
+        for (int x = lo; x < hi; ++x) s_owner[x] = o;
       }
-      const int i = lo, k = pp - s_off[i];
-      int r = 0, kb = 0;  // range of candidate k and where that range begins
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int e = s_cum[q][i];
-        if (k >= e) { r = q + 1; kb = e; }
+      __syncthreads();
+      // ---- phase 2: one candidate test per thread and iteration
+      const int tn = min(kTile, P - tile);
+      for (int pp = threadIdx.x; pp < tn; pp += kPC) {
+        const int o = s_owner[pp];
+        const int i = (o * 10923) >> 16;  // o / 6 for o < 1536
+        const bool dyn_cand = o - i * 6 >= 3;
+        const int q = tile + pp + s_delta[o];
+        const int4 ot = __ldg((dyn_cand ? srt : p.ssorted) + q);
+        const int4 me = s_me[i];
+        const int a = me.y;
+        if (dyn_cand) {
+          if (ot.y == a) continue;
+          if ((all || fl_changed(ot.z)) && ot.y < a) continue;  // that agent owns the pair
+        }
+        ++tests;
+        if (!within_xy(me.x, ot.x, p)) continue;
+        const FloorDev& fd = p.floors[fl_floor(me.z)];  // cells are per floor: the candidate is on the same one
+        if (!loc_rule_ordered(fd, a, fl_loc(me.z), ot.y, fl_loc(ot.z))) continue;
+        const uint32_t run = run_length(p, me.w, ot.w, t);
+        hits += run;
+        ++runs;
+        if (buffered && nh < kHitSlots) {
+          ContactRec rec;
+          rec.a1 = (uint32_t)min(a, ot.y); rec.a2 = (uint32_t)max(a, ot.y);
+          rec.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
+          rec.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
+                         (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
+          mine[nh++] = rec;
+        } else {
+          on_contact(p, t, me, ot, run, false, sub, true);
+        }
       }
-      const int q = s_qs[r][i] + (k - kb);
-      const bool dyn_cand = r >= 3;
-      const int4 ot = dyn_cand ? srt[q] : p.ssorted[q];
-      const int4 me = s_me[i];
-      const int a = me.y;
-      if (dyn_cand) {
-        if (ot.y == a) continue;
-        if ((all || fl_changed(ot.z)) && ot.y < a) continue;  // that agent owns the pair
-      }
-      ++tests;
-      if (!within_xy(me.x, ot.x, p)) continue;
-      const FloorDev& fd = p.floors[fl_floor(me.z)];
-      if (fl_floor(ot.z) != fl_floor(me.z)) continue;  // cannot happen (cells are per floor); cheap guard
-      if (!loc_rule_ordered(fd, a, fl_loc(me.z), ot.y, fl_loc(ot.z))) continue;
-      const uint32_t run = run_length(p, me.w, ot.w, t);
-      hits += run;
-      ++runs;
-      if (buffered && nh < kHitSlots) {
-        ContactRec rec;
-        rec.a1 = (uint32_t)min(a, ot.y); rec.a2 = (uint32_t)max(a, ot.y);
-        rec.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
-        rec.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
-                       (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
-        mine[nh++] = rec;
-      } else {
-        on_contact(p, t, me, ot, run, false, sub, true);
-      }
+      __syncthreads();  // the tile map is rewritten
     }
     if (buffered) {
       // one reservation for the whole warp
@@ -1267,30 +1345,51 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
 // 24 blocks per sub-buffer 2.08e10 agent-steps/s, 96: 2.27e10, 256: 2.37e10)
 constexpr int kAccBlocksPerSub = 256;
 
+// kAccIlp records per thread and iteration: the loads of all of them (records, previous-step records,
+// first slot probes) are issued before any is consumed -- the kernel is bound by memory latency at full
+// occupancy, so the independent chains in flight per thread are what sets its rate.
+template <int K>
 __global__ void __launch_bounds__(256) k_accumulate(Params p, int t_begin) {
   const int sub = blockIdx.x % kSubBuffers, part = blockIdx.x / kSubBuffers;
   const unsigned long long n = min(p.cbuf_count[sub * kCounterStride], p.cbuf_sub_cap);
   const ContactRec* buf = p.cbuf + (unsigned long long)sub * p.cbuf_sub_cap;
   const unsigned long long stride = (unsigned long long)(gridDim.x / kSubBuffers) * blockDim.x;
-  for (unsigned long long i = (unsigned long long)part * blockDim.x + threadIdx.x; i < n; i += stride) {
-    ContactRec r = buf[i];
-    const uint32_t t_rel = r.t_run & 0xfffu, run = (r.t_run >> 12) + 1u;
-    const uint32_t t = (uint32_t)t_begin + t_rel;
-    bool was = r.bucket >> 31;
-    int4 r1 = make_int4(0, 0, 0, 0), r2 = r1;
-    const bool late = (r.bucket >> 30) & 1;
-    if (late) {  // both agents' records of step t-1
-      r1 = prev_rec(p, t_rel, r.a1);
-      r2 = prev_rec(p, t_rel, r.a2);
+  for (unsigned long long i0 = (unsigned long long)part * blockDim.x + threadIdx.x; i0 < n; i0 += stride * K) {
+    ContactRec r[K];
+    bool live[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      live[k] = i0 + k * stride < n;
+      if (live[k]) r[k] = buf[i0 + k * stride];
     }
-    // the histogram reduction and the table probe are independent: issue both, then update
-    atomicAdd(p.hist + (r.bucket & 0x3fffffffu), (unsigned long long)run);
-    unsigned long long acc;
-    unsigned long long h = pair_slot(p, ((unsigned long long)r.a1 << 32) | r.a2, &acc);
-    if (h == ~0ULL) continue;
-    if (late) was = contact_eval(p, r1, r2);
-    uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
-    pair_apply(p, h, acc, first, run, was ? 0u : 1u, r.a1, r.a2);
+    int4 r1[K], r2[K];
+    unsigned long long h[K];
+    ulonglong2 e0[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (!live[k]) continue;
+      // the histogram reduction, the previous-step records and the table probe are independent: issue all
+      atomicAdd(p.hist + (r[k].bucket & 0x3fffffffu), (unsigned long long)((r[k].t_run >> 12) + 1u));
+      if ((r[k].bucket >> 30) & 1) {  // both agents' records of step t-1
+        r1[k] = prev_rec(p, r[k].t_run & 0xfffu, r[k].a1);
+        r2[k] = prev_rec(p, r[k].t_run & 0xfffu, r[k].a2);
+      }
+      h[k] = mix64(((unsigned long long)r[k].a1 << 32) | r[k].a2) & p.pair_mask;
+      e0[k] = load_entry(&p.pairs[h[k]]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (!live[k]) continue;
+      const uint32_t t_rel = r[k].t_run & 0xfffu, run = (r[k].t_run >> 12) + 1u;
+      const uint32_t t = (uint32_t)t_begin + t_rel;
+      bool was = r[k].bucket >> 31;
+      unsigned long long acc;
+      const unsigned long long slot = pair_slot_from(p, ((unsigned long long)r[k].a1 << 32) | r[k].a2, h[k], e0[k], &acc);
+      if (slot == ~0ULL) continue;
+      if ((r[k].bucket >> 30) & 1) was = contact_eval(p, r1[k], r2[k]);
+      uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
+      pair_apply(p, slot, acc, first, run, was ? 0u : 1u, r[k].a1, r[k].a2);
+    }
   }
 }
 
@@ -1646,15 +1745,42 @@ __global__ void k_unpack_durations(const unsigned long long* agent_dur, int N, u
 
 // Records of another engine (rank) into this table.  Only the pair table is touched: per-agent
 // contact seconds are reduced separately (all-reduce of the counters), see the header.
-__global__ void k_merge_pairs(Params p, const citam_pair* in, unsigned long long n, int* bad) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  citam_pair r = in[i];
-  if (r.a1 >= r.a2 || r.a2 >= (uint32_t)p.N || r.duration > 0xffffffULL || r.n_events > 0xffffu) { atomicOr(bad, 1); return; }
-  unsigned long long old;
-  unsigned long long h = pair_slot(p, ((unsigned long long)r.a1 << 32) | r.a2, &old);
-  if (h == ~0ULL) return;
-  pair_apply_acc(p, h, old, r.first_step > 0xFFFFFFu ? NO_STEP : r.first_step, r.duration, r.n_events);
+// kMergeIlp records per thread, first probes of all of them in flight together (latency-bound random inserts).
+constexpr int kMergeIlp = 4;
+__global__ void __launch_bounds__(256) k_merge_pairs(Params p, const citam_pair* in, unsigned long long n, int* bad) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  citam_pair r[kMergeIlp];
+  bool live[kMergeIlp];
+  unsigned long long h[kMergeIlp];
+  ulonglong2 e0[kMergeIlp];
+  uint32_t mx = 0;
+#pragma unroll
+  for (int k = 0; k < kMergeIlp; ++k) {
+    live[k] = i0 + k * stride < n;
+    if (!live[k]) continue;
+    r[k] = in[i0 + k * stride];
+    if (r[k].a1 >= r[k].a2 || r[k].a2 >= (uint32_t)p.N || r[k].duration > 0xffffffULL || r[k].n_events > 0xffffu) {
+      atomicOr(bad, 1);
+      live[k] = false;
+      continue;
+    }
+    h[k] = mix64(((unsigned long long)r[k].a1 << 32) | r[k].a2) & p.pair_mask;
+    e0[k] = load_entry(&p.pairs[h[k]]);
+  }
+#pragma unroll
+  for (int k = 0; k < kMergeIlp; ++k) {
+    if (!live[k]) continue;
+    unsigned long long old;
+    const unsigned long long slot = pair_slot_from(p, ((unsigned long long)r[k].a1 << 32) | r[k].a2, h[k], e0[k], &old);
+    if (slot == ~0ULL) continue;
+    const uint32_t first = r[k].first_step > 0xFFFFFFu ? NO_STEP : r[k].first_step;
+    if (first != NO_STEP) mx = max(mx, first);
+    pair_apply_acc(p, slot, old, first, r[k].duration, r[k].n_events);
+  }
+  // the largest first-contact step merged so far (sort key width of the ordered export)
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&p.ctr->merged_max_step, (unsigned long long)mx);
 }
 
 __global__ void k_merge_coords(Params p, const citam_coord* in, unsigned long long n) {
@@ -1698,6 +1824,7 @@ struct citam_engine {
   int2* window_d = nullptr;  // k_agent_windows
   bool window_dirty = true;
   int acc_blocks = kAccBlocksPerSub;  // k_accumulate blocks per sub-buffer (CITAM_ACC_BLOCKS overrides)
+  int acc_ilp = 2;  // records per thread and iteration in k_accumulate (CITAM_ACC_ILP: 1, 2 or 4)
   bool explicit_states = false;  // citam_step_states in progress: states come from the caller, no windows
   bool have_itin = false;
 
@@ -1714,7 +1841,7 @@ struct citam_engine {
   int4* srec_buf[2] = {nullptr, nullptr};
   uint32_t* cls_buf[2] = {nullptr, nullptr};
   int4* ssorted = nullptr;
-  uint32_t *scells = nullptr, *dyn_agent = nullptr, *dyn_count = nullptr;
+  uint32_t *scells = nullptr, *dyn_agent = nullptr, *dyn_count = nullptr, *seg_cur = nullptr;
   int dtotal_cells = 0, dcells_stride = 4;
   bool split = false;  // the chunk being processed uses the split pipeline
   bool no_fast_stats = false;  // CITAM_NO_FAST_STATS=1: statistics always from the pass over the pair table (tests)
@@ -1874,7 +2001,7 @@ static Params make_params(citam_engine* e) {
   p.dtotal_cells = e->dtotal_cells; p.dcells_stride = e->dcells_stride;
   if (e->split) {
     p.cls = e->cls_buf[e->cur]; p.srec = e->srec_buf[e->cur];
-    p.ssorted = e->ssorted; p.scells = e->scells; p.dyn_agent = e->dyn_agent; p.dyn_count = e->dyn_count;
+    p.ssorted = e->ssorted; p.scells = e->scells; p.dyn_agent = e->dyn_agent; p.dyn_count = e->dyn_count; p.seg_cur = e->seg_cur;
   }
   p.ctr = e->ctr_d;
   return p;
@@ -1889,8 +2016,8 @@ static void free_chunk(citam_engine* e) {
   cudaFree(e->sorted); cudaFree(e->chg_list); cudaFree(e->chg_count); cudaFree(e->part_sums);
   e->chg_list = e->chg_count = e->part_sums = nullptr;
   for (int b = 0; b < 2; ++b) { cudaFree(e->srec_buf[b]); cudaFree(e->cls_buf[b]); e->srec_buf[b] = nullptr; e->cls_buf[b] = nullptr; }
-  cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count);
-  e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = nullptr;
+  cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count); cudaFree(e->seg_cur);
+  e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = e->seg_cur = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -1975,6 +2102,8 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->scells, sizeof(uint32_t) * (size_t)e->cells_stride));
   CK(cudaMalloc(&e->dyn_agent, sizeof(uint32_t) * n));
   CK(cudaMalloc(&e->dyn_count, sizeof(uint32_t)));
+  CK(cudaMalloc(&e->seg_cur, sizeof(uint32_t) * n));
+  CK(cudaMemsetAsync(e->seg_cur, 0, sizeof(uint32_t) * n, e->stream));
   e->S = S;
   return CITAM_OK;
 }
@@ -1998,6 +2127,7 @@ static void launch_scan(citam_engine* e, uint32_t* cells, int stride, int n, int
   Timed tm(e, CITAM_K_SCAN);
   const int n4 = (n + 3) >> 2;
   int parts = std::max(1, std::min(kMaxScanParts, std::min((296 + rows - 1) / rows, (n4 + 4095) / 4096)));
+  if (rows >= 64 && n4 <= 16384) parts = 1;  // enough rows to fill the machine: one block per row, no second pass
   int part_len4 = (n4 + parts - 1) / parts;
   parts = (n4 + part_len4 - 1) / part_len4;
   k_scan<<<dim3(parts, rows), kScanThreads, 0, e->stream>>>(cells, stride, n, part_len4, e->part_sums);
@@ -2014,7 +2144,10 @@ static int launch_accumulate(citam_engine* e, const Params& p, int t_begin) {
   CK(cudaStreamWaitEvent(e->stream2, e->ev_built[e->cur], 0));
   {
     Timed tm(e, CITAM_K_ACCUMULATE, e->stream2, true);
-    k_accumulate<<<kSubBuffers * e->acc_blocks, 256, 0, e->stream2>>>(p, t_begin);
+    const int nb = kSubBuffers * e->acc_blocks;
+    if (e->acc_ilp >= 4) k_accumulate<4><<<nb, 256, 0, e->stream2>>>(p, t_begin);
+    else if (e->acc_ilp >= 2) k_accumulate<2><<<nb, 256, 0, e->stream2>>>(p, t_begin);
+    else k_accumulate<1><<<nb, 256, 0, e->stream2>>>(p, t_begin);
     k_reset_cbuf<<<1, kSubBuffers, 0, e->stream2>>>(p.cbuf_count);
     e->launches++;
   }
@@ -2088,7 +2221,7 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
   {
     Timed tm(e, CITAM_K_SCATTER);
     k_scatter_static<<<gN, 256, 0, e->stream>>>(p);
-    k_scatter_dyn<<<wide, 256, 0, e->stream>>>(p, steps, tb);
+    k_scatter_dyn<<<dim3(32, steps), 256, 0, e->stream>>>(p, steps);
     k_select_changed_dyn<<<dim3(16, steps), 256, 0, e->stream>>>(p, steps, first ? 0 : -1);
     e->launches += 2;
   }
@@ -2186,6 +2319,7 @@ static int maybe_grow_pairs(citam_engine* e, bool now) {
 
 static int create_impl(citam_engine* e, const citam_config* cfg) {
   if (const char* g = getenv("CITAM_ACC_BLOCKS")) e->acc_blocks = std::max(1, atoi(g));
+  if (const char* g = getenv("CITAM_ACC_ILP")) e->acc_ilp = atoi(g);
   if (const char* g = getenv("CITAM_NO_SPLIT")) e->no_split = atoi(g) != 0;
   if (const char* g = getenv("CITAM_NO_FAST_STATS")) e->no_fast_stats = atoi(g) != 0;
   e->cfg = *cfg;
@@ -3096,14 +3230,19 @@ int citam_merge_pairs_device(citam_engine* e, const citam_pair* pairs_device, ui
   {
     Timed tm(e, CITAM_K_FINALIZE);
     e->counters_match = false;
-    k_merge_pairs<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, pairs_device, n, e->flag_d);
+    const unsigned long long per_block = 256ULL * kMergeIlp;
+    k_merge_pairs<<<(unsigned)((n + per_block - 1) / per_block), 256, 0, e->stream>>>(p, pairs_device, n, e->flag_d);
   }
   CK(cudaGetLastError());
   int bad = 0;
   rc = read_flag(e, &bad);
   if (rc) return rc;
   if (bad) return fail(CITAM_ERR_INVALID, "a merged pair record is malformed (need a1 < a2 < n_agents, duration < 2^24, events < 2^16)");
-  e->max_step = 0xFFFFFFu;  // merged first-contact steps are not bounded by what this engine ran
+  // merged first-contact steps are not bounded by what this engine ran: the kernel kept their maximum
+  DevCounters c;
+  CK(cudaMemcpyAsync(&c, e->ctr_d, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->max_step = std::max<uint32_t>(e->max_step, (uint32_t)std::min<unsigned long long>(0xFFFFFEu, c.merged_max_step) + 1u);
   return check_overflow(e);
 }
 

@@ -203,6 +203,10 @@ class ShardedRun:
 
         dist = _dist()
         eng, G = self.engine, self.world
+        if (eng.n_agents - 1) * self.T >= 1 << 40:
+            raise ValueError("(n_agents - 1) x total_timesteps must stay below 2^40 (per-agent counter width)")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
         ptr, n = eng.agent_durations_device()
         dist.all_reduce(device_tensor(ptr, n))
         hptr, hn = eng.hist_device()
@@ -214,10 +218,12 @@ class ShardedRun:
             for r in range(G):
                 if r != self.rank:
                     eng.merge(np.zeros(0, PAIR), gc[r])
+        ev[1].record()
         # pair table: partition -> all-to-all -> merge
         n_local = eng.pair_count()
         send = torch.empty((max(1, n_local), 3), dtype=torch.int64, device="cuda")
         counts = eng.partition_pairs_device(send.data_ptr(), n_local, G)
+        ev[2].record()
         send_counts = torch.from_numpy(counts.astype(np.int64)).cuda()
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts)
@@ -226,19 +232,30 @@ class ShardedRun:
         n_recv = int(sum(out_split))
         recv = torch.empty((max(1, n_recv), 3), dtype=torch.int64, device="cuda")
         dist.all_to_all_single(recv[:n_recv], send[:n_local], out_split, in_split)
+        ev[3].record()
         torch.cuda.synchronize()
         eng.clear_pairs()
         eng.merge_pairs_device(recv.data_ptr(), n_recv)
+        ev[4].record()
         del send, recv
+        sums = self._statistics(reduced=True)
+        ev[5].record()
+        torch.cuda.synchronize()
         self.info = {
             "pairs_local_before": int(n_local), "pairs_received": n_recv, "pairs_after": eng.pair_count(),
             "a2a_bytes_sent": int(24 * (n_local - int(counts[self.rank]))),
             "allreduce_bytes": int(8 * n + 8 * hn),
+            "allreduce_ms": ev[0].elapsed_time(ev[1]), "partition_ms": ev[1].elapsed_time(ev[2]),
+            "all_to_all_ms": ev[2].elapsed_time(ev[3]), "clear_and_merge_ms": ev[3].elapsed_time(ev[4]),
+            "statistics_ms": ev[4].elapsed_time(ev[5]),
         }
-        return self.statistics()
+        return sums
 
     def statistics(self) -> Dict[str, int]:
         """The run's statistics sums from the rank-partitioned pair table."""
+        return self._statistics(reduced=bool(self.info))
+
+    def _statistics(self, reduced: bool) -> Dict[str, int]:
         import torch
 
         dist = _dist()
@@ -246,7 +263,7 @@ class ShardedRun:
         # after `reduce` the per-agent counter words are the whole run's (seconds | events << 40): the
         # sums need no pass over the pair table; n_pairs is this rank's share
         fast = None
-        if self.info:
+        if reduced:
             try:
                 fast = eng.statistics_counters()
             except CitamCapacityError:

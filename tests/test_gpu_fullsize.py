@@ -1,8 +1,10 @@
 """GPU parity at BASELINE.json's full sizes.
 
 config 2 (10^4 agents, one floor, the whole 28 800-step day) is compared table for table with the C
-oracle.  config 3 (10^6 agents, 10 floors) is compared with the C oracle on a window of the day,
-and checked through size-independent properties: conservation (every contact-step is in exactly one
+oracle.  config 3 (10^6 agents, 10 floors) is compared with the C oracle on a 160-step window and on
+2 400 contiguous steps of the day (many chunks, contact runs crossing chunk borders, both step
+pipelines), config 5 (2 x 10^5 agents crowded on one floor) on a 96-step window, and config 3 is
+checked through size-independent properties: conservation (every contact-step is in exactly one
 pair, two agents' counters and one coordinate bucket), additivity over time blocks run on different
 engines and merged, and independence of the chunking."""
 import numpy as np
@@ -86,4 +88,48 @@ def test_config3_million_agents_window_and_invariants():
     merged = _arrays(a)
     _same((merged[0], merged[1], merged[2] + da.astype(np.int64)), got)
     a.close()
+    eng.close()
+
+
+def test_config3_million_agents_2400_contiguous_steps_equal_oracle(monkeypatch):
+    """10^6 agents through 2 400 contiguous steps in the middle of the first shift: ~19 chunks of the
+    split pipeline, contact runs that span them, against the C oracle table for table."""
+    from citam_b200 import synthetic as S
+    from citam_b200.engine import DeviceEngine
+
+    fac, seg_off, segs, p = S.make_config("config3", seed=0)
+    N, t0, t1 = p["n_agents"], 3_000, 5_400
+    g = grid_oracle_for(fac.geometry, 6.0, seg_off, segs)
+    g.run(t0, t1, 16)
+    want = _arrays(g)
+    eng = DeviceEngine(N, p["n_floors"], 6.0, pair_capacity=1 << 28)
+    eng.load_geometry(fac.geometry)
+    eng.load_segments(seg_off, segs)
+    eng.run(t0, t1)
+    got = _arrays(eng)
+    _same(got, want)
+    assert eng.counters()["contact_steps"] == g.contact_steps
+    sums = eng.statistics_sums()
+    assert sums["n_pairs"] == len(want[0]) and sums["total_duration"] == int(want[0]["duration"].sum())
+    eng.close()
+
+
+def test_config5_dense_floor_window_equals_oracle():
+    """2 x 10^5 agents on one floor, 85 % of them bound for shared destinations (tens of neighbours
+    within the contact distance each): a 96-step window against the C oracle."""
+    from citam_b200 import synthetic as S
+    from citam_b200.engine import DeviceEngine
+
+    fac, seg_off, segs, p = S.make_config("config5", seed=0)
+    N, t0, t1 = p["n_agents"], 9_000, 9_096
+    g = grid_oracle_for(fac.geometry, 6.0, seg_off, segs)
+    g.run(t0, t1, 16)
+    want = _arrays(g)
+    eng = DeviceEngine(N, p["n_floors"], 6.0, pair_capacity=1 << 28)
+    eng.load_geometry(fac.geometry)
+    eng.load_segments(seg_off, segs)
+    eng.run(t0, t1)
+    got = _arrays(eng)
+    _same(got, want)
+    assert eng.counters()["contact_steps"] == g.contact_steps
     eng.close()
