@@ -624,8 +624,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(uint32_t* cells, int stri
 __global__ void __launch_bounds__(256) k_scan_add(uint32_t* cells, int stride, int n, int part_len4,
                                                   const uint32_t* part_sums) {
   const int part = blockIdx.x + 1;  // piece 0 needs no offset
-  uint32_t off = 0;
-  for (int q = 0; q < part; ++q) off += part_sums[blockIdx.y * (gridDim.x + 1) + q];
+  __shared__ uint32_t s_off;
+  if (threadIdx.x < 32) {  // at most kMaxScanParts = 32 pieces: one load per lane, shuffle sum
+    uint32_t v = (int)threadIdx.x < part ? part_sums[blockIdx.y * (gridDim.x + 1) + threadIdx.x] : 0u;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (threadIdx.x == 0) s_off = v;
+  }
+  __syncthreads();
+  const uint32_t off = s_off;
   if (off == 0) return;
   uint4* c4 = reinterpret_cast<uint4*>(cells + (size_t)blockIdx.y * stride);
   const int n4 = (n + 3) >> 2;
@@ -1167,18 +1173,70 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed(Params p, int t_begin, in
 // static-static pairs are k_pairs').
 constexpr int kTile = 4096;  // candidates per tile of the flat index space
 
-__global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_begin, int rows /* S */, int all_row) {
-  __shared__ ContactRec hitbuf[kPC * kHitSlots];
-  __shared__ int4 s_me[kPC];
-  __shared__ int s_delta[kPC * 6];        // candidate position = flat index + s_delta[agent * 6 + range]
+// Candidates that passed the distance test wait in a per-warp queue and are finished 32 at a time by
+// all lanes of the warp (space rule, run length, record, ONE reservation in the contact buffer per 32
+// records): one candidate in six passes, so finishing each where it was found left 27 of 32 lanes idle
+// through a quarter of the kernel's instructions.
+struct HitQueue {
+  int4 ot[64];       // the candidate's sorted record
+  uint16_t who[64];  // the changed agent's index in the batch
+};
+
+__device__ __forceinline__ void drain_hits(const Params& p, HitQueue& q, const int4* s_me, int count, uint32_t t, int sub,
+                                           unsigned long long& hits, unsigned long long& runs) {
+  const int lane = threadIdx.x & 31;
+  bool good = false;
+  ContactRec rec;
+  int4 me = make_int4(0, 0, 0, 0), ot = me;
+  uint32_t run = 0;
+  if (lane < count) {
+    ot = q.ot[lane];
+    me = s_me[q.who[lane]];
+    const FloorDev& fd = p.floors[fl_floor(me.z)];  // cells are per floor: the candidate is on the same one
+    good = loc_rule_ordered(fd, me.y, fl_loc(me.z), ot.y, fl_loc(ot.z));
+    if (good) {
+      run = run_length(p, me.w, ot.w, t);
+      hits += run;
+      ++runs;
+      rec.a1 = (uint32_t)min(me.y, ot.y); rec.a2 = (uint32_t)max(me.y, ot.y);
+      rec.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
+      rec.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
+                     (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, good);
+  if (m == 0) return;
+  bool stored = false;
+  if (p.cbuf != nullptr) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&p.cbuf_count[sub * kCounterStride], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1u));
+    if (good && base < p.cbuf_sub_cap) {
+      p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + base] = rec;
+      stored = true;
+    }
+  }
+  if (good && !stored) {  // no contact buffer, or it is full (k_accumulate clamps the count): apply here
+    const bool was = contact_prev(p, rec.t_run & 0xfffu, rec.a1, rec.a2);
+    const uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
+    pair_upsert(p, rec.a1, rec.a2, first, run, was ? 0u : 1u);
+    coord_upsert_rel(p, fl_floor(me.z), xy_x(me.x) + xy_x(ot.x), xy_y(me.x) + xy_y(ot.x), (unsigned long long)run);
+  }
+}
+
+template <int kPS>
+__global__ void __launch_bounds__(kPS, 1024 / kPS) k_pairs_changed_split(Params p, int t_begin, int rows /* S */, int all_row) {
+  __shared__ int4 s_me[kPS];
+  __shared__ HitQueue s_queue[kPS / 32];
+  __shared__ int s_delta[kPS * 6];        // candidate position = flat index + s_delta[agent * 6 + range]
   __shared__ uint16_t s_owner[kTile];     // agent * 6 + range of a flat index (relative to the tile)
-  __shared__ int s_warp[kPC / 32];
+  __shared__ int s_warp[kPS / 32];
   __shared__ int s_total;
   __shared__ int s_void;
   const int row = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = p.chg_count[row * 32];
-  if (blockIdx.x * kPC >= n) return;
+  if (blockIdx.x * kPS >= n) return;
   if (threadIdx.x == 0)
     s_void = (*(volatile unsigned long long*)&p.ctr->overflow & (OVF_PAIR | OVF_COORD | OVF_FIELD)) != 0;
   __syncthreads();
@@ -1188,11 +1246,11 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
   const int4* srt = p.sorted + (size_t)row * p.N;
   const uint32_t t = (uint32_t)(t_begin + row);
   const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
-  const bool buffered = p.cbuf != nullptr;
   const bool all = row == all_row;
-  ContactRec* mine = hitbuf + threadIdx.x * kHitSlots;
+  HitQueue& queue = s_queue[wid];
+  int qn = 0;  // queued hits of this warp (the same in all its lanes)
   unsigned long long tests = 0, hits = 0, runs = 0;
-  for (uint32_t base = blockIdx.x * kPC; base < n; base += gridDim.x * kPC) {
+  for (uint32_t base = blockIdx.x * kPS; base < n; base += gridDim.x * kPS) {
     // ---- phase 1: one thread per agent describes its six candidate ranges
     const uint32_t idx = base + threadIdx.x;
     int total = 0;
@@ -1248,10 +1306,9 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
         o += len[r];
       }
     }
-    if (threadIdx.x == kPC - 1) s_total = woff + inc;
+    if (threadIdx.x == kPS - 1) s_total = woff + inc;
     __syncthreads();
     const int P = s_total;
-    int nh = 0;
     for (int tile = 0; tile < P; tile += kTile) {
       // ---- the tile's flat index -> (agent, range) map
 #pragma unroll
@@ -1261,65 +1318,54 @@ __global__ void __launch_bounds__(kPC) k_pairs_changed_split(Params p, int t_beg
         for (int x = lo; x < hi; ++x) s_owner[x] = o;
       }
       __syncthreads();
-      // ---- phase 2: one candidate test per thread and iteration
+      // ---- phase 2: one candidate test per thread and iteration (the same trip count for the whole block)
       const int tn = min(kTile, P - tile);
-      for (int pp = threadIdx.x; pp < tn; pp += kPC) {
-        const int o = s_owner[pp];
-        const int i = (o * 10923) >> 16;  // o / 6 for o < 1536
-        const bool dyn_cand = o - i * 6 >= 3;
-        const int q = tile + pp + s_delta[o];
-        const int4 ot = __ldg((dyn_cand ? srt : p.ssorted) + q);
-        const int4 me = s_me[i];
-        const int a = me.y;
-        if (dyn_cand) {
-          if (ot.y == a) continue;
-          if ((all || fl_changed(ot.z)) && ot.y < a) continue;  // that agent owns the pair
+      for (int pp0 = 0; pp0 < tn; pp0 += kPS) {
+        const int pp = pp0 + threadIdx.x;
+        bool hit = false;
+        int4 ot = make_int4(0, 0, 0, 0);
+        int i = 0;
+        if (pp < tn) {
+          const int o = s_owner[pp];
+          i = (o * 10923) >> 16;  // o / 6 for o < 1536
+          const bool dyn_cand = o - i * 6 >= 3;
+          ot = __ldg((dyn_cand ? srt : p.ssorted) + (tile + pp + s_delta[o]));
+          const int4 me = s_me[i];
+          // a dynamic candidate: not the agent itself, and not a pair the other agent owns
+          const bool skip = dyn_cand && (ot.y == me.y || ((all || fl_changed(ot.z)) && ot.y < me.y));
+          if (!skip) {
+            ++tests;
+            hit = within_xy(me.x, ot.x, p);
+          }
         }
-        ++tests;
-        if (!within_xy(me.x, ot.x, p)) continue;
-        const FloorDev& fd = p.floors[fl_floor(me.z)];  // cells are per floor: the candidate is on the same one
-        if (!loc_rule_ordered(fd, a, fl_loc(me.z), ot.y, fl_loc(ot.z))) continue;
-        const uint32_t run = run_length(p, me.w, ot.w, t);
-        hits += run;
-        ++runs;
-        if (buffered && nh < kHitSlots) {
-          ContactRec rec;
-          rec.a1 = (uint32_t)min(a, ot.y); rec.a2 = (uint32_t)max(a, ot.y);
-          rec.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
-          rec.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
-                         (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
-          mine[nh++] = rec;
-        } else {
-          on_contact(p, t, me, ot, run, false, sub, true);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          if (hit) {
+            const int pos = qn + __popc(m & ((1u << lane) - 1u));
+            queue.ot[pos] = ot;
+            queue.who[pos] = (uint16_t)i;
+          }
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32) {
+            drain_hits(p, queue, s_me, 32, t, sub, hits, runs);
+            __syncwarp();
+            int4 mv = make_int4(0, 0, 0, 0);
+            uint16_t mw = 0;
+            if (32 + lane < qn) { mv = queue.ot[32 + lane]; mw = queue.who[32 + lane]; }
+            __syncwarp();
+            if (32 + lane < qn) { queue.ot[lane] = mv; queue.who[lane] = mw; }
+            qn -= 32;
+            __syncwarp();
+          }
         }
       }
       __syncthreads();  // the tile map is rewritten
     }
-    if (buffered) {
-      // one reservation for the whole warp
-      int off = nh;
-      for (int d = 1; d < 32; d <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, off, d);
-        if (lane >= d) off += v;
-      }
-      const int wtotal = __shfl_sync(0xffffffffu, off, 31);
-      if (wtotal > 0) {
-        unsigned long long wbase = 0;
-        if (lane == 31) wbase = atomicAdd(&p.cbuf_count[sub * kCounterStride], (unsigned long long)wtotal);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31) + (unsigned long long)(off - nh);
-        for (int j = 0; j < nh; ++j) {
-          if (wbase + j < p.cbuf_sub_cap) {
-            p.cbuf[(unsigned long long)sub * p.cbuf_sub_cap + wbase + j] = mine[j];
-          } else {  // sub-buffer full: apply inline (k_accumulate clamps the count)
-            const ContactRec rr = mine[j];
-            const uint32_t rt = (uint32_t)p.chunk_begin + (rr.t_run & 0xfffu), rrun = (rr.t_run >> 12) + 1u;
-            bool was = contact_prev(p, rr.t_run & 0xfffu, rr.a1, rr.a2);
-            uint32_t first = (!was || (int32_t)rt == p.range_begin) ? rt : NO_STEP;
-            pair_upsert(p, rr.a1, rr.a2, first, rrun, was ? 0u : 1u);
-            atomicAdd(p.hist + (rr.bucket & 0x3fffffffu), (unsigned long long)rrun);
-          }
-        }
-      }
+    // the batch's agents (s_me) are replaced next: finish what is queued
+    if (qn) {
+      drain_hits(p, queue, s_me, qn, t, sub, hits, runs);
+      qn = 0;
     }
     __syncthreads();  // the batch's shared arrays are reused
   }
@@ -1824,6 +1870,7 @@ struct citam_engine {
   int2* window_d = nullptr;  // k_agent_windows
   bool window_dirty = true;
   int acc_blocks = kAccBlocksPerSub;  // k_accumulate blocks per sub-buffer (CITAM_ACC_BLOCKS overrides)
+  int pair_tpb = 128;  // threads per block of k_pairs_changed_split (CITAM_PAIR_TPB: 128 or 256)
   int acc_ilp = 2;  // records per thread and iteration in k_accumulate (CITAM_ACC_ILP: 1, 2 or 4)
   bool explicit_states = false;  // citam_step_states in progress: states come from the caller, no windows
   bool have_itin = false;
@@ -2213,7 +2260,7 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
     Timed tm(e, CITAM_K_EXPAND_BIN);
     k_classify<<<gN, 256, 0, e->stream>>>(p, tb, steps);
     e->launches++;
-    k_expand_dyn<<<wide * 2, 128, 0, e->stream>>>(p, tb - 1, rows, 16);
+    k_expand_dyn<<<wide * 4, 128, 0, e->stream>>>(p, tb - 1, rows, 8);
   }
   launch_scan(e, e->scells, e->cells_stride, e->total_cells + 1, 1);
   launch_scan(e, e->cells, e->dcells_stride, e->dtotal_cells + 1, steps);
@@ -2221,8 +2268,8 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
   {
     Timed tm(e, CITAM_K_SCATTER);
     k_scatter_static<<<gN, 256, 0, e->stream>>>(p);
-    k_scatter_dyn<<<dim3(32, steps), 256, 0, e->stream>>>(p, steps);
-    k_select_changed_dyn<<<dim3(16, steps), 256, 0, e->stream>>>(p, steps, first ? 0 : -1);
+    k_scatter_dyn<<<dim3(128, steps), 256, 0, e->stream>>>(p, steps);
+    k_select_changed_dyn<<<dim3(64, steps), 256, 0, e->stream>>>(p, steps, first ? 0 : -1);
     e->launches += 2;
   }
   {
@@ -2231,7 +2278,8 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
       k_pairs<<<dim3(gN, 1), 256, 0, e->stream>>>(p, tb, 1, 1, 1);
       e->launches++;
     }
-    k_pairs_changed_split<<<dim3(64, steps), kPC, 0, e->stream>>>(p, tb, steps, first ? 0 : -1);
+    if (e->pair_tpb == 128) k_pairs_changed_split<128><<<dim3(128, steps), 128, 0, e->stream>>>(p, tb, steps, first ? 0 : -1);
+    else k_pairs_changed_split<256><<<dim3(64, steps), 256, 0, e->stream>>>(p, tb, steps, first ? 0 : -1);
   }
   int rc = launch_accumulate(e, p, tb);
   if (rc) return rc;
@@ -2320,6 +2368,7 @@ static int maybe_grow_pairs(citam_engine* e, bool now) {
 static int create_impl(citam_engine* e, const citam_config* cfg) {
   if (const char* g = getenv("CITAM_ACC_BLOCKS")) e->acc_blocks = std::max(1, atoi(g));
   if (const char* g = getenv("CITAM_ACC_ILP")) e->acc_ilp = atoi(g);
+  if (const char* g = getenv("CITAM_PAIR_TPB")) e->pair_tpb = atoi(g);
   if (const char* g = getenv("CITAM_NO_SPLIT")) e->no_split = atoi(g) != 0;
   if (const char* g = getenv("CITAM_NO_FAST_STATS")) e->no_fast_stats = atoi(g) != 0;
   e->cfg = *cfg;
