@@ -180,9 +180,27 @@ struct Params {
   uint32_t* dyn_agent;      // [N] agent of dynamic index j
   uint32_t* dyn_count;      // dynamic agents of this chunk
   uint32_t* seg_cur;        // [N] per agent: 1 + index (inside its segments) of the segment k_classify last found
+  // still intervals of DYNAMIC agents: a stay of >= kStillMin steps inside the chunk is one more entry
+  // of the static array, valid from `since` (state word bits 16-23: since - (chunk_begin - 1)) until
+  // `until`; the agent is then binned per step only at the steps no such entry covers
+  int4* ient;               // [(S / kStillMin + 1) * N] {xy, agent, state word | since << 16, until}
+  uint32_t* ient_rank;      // rank of the entry in its fine cell
+  uint32_t* ient_count;
+  uint8_t* dmask;           // [S][N] by dynamic index: 1 = the agent is binned at this step
+  uint32_t* need;           // [N] by dynamic index: bit g = rows 8g .. 8g+7 of the chunk hold a step at which the agent
+                            // is binned, or the record before one (all other row groups are skipped by every kernel)
+  int32_t chunk_steps;      // steps of the chunk being processed
+  int32_t still_min;        // shortest stay that becomes an entry (>= kStillMin; larger than a chunk: none does)
   DevCounters* ctr;
 };
 constexpr uint32_t kClsOut = 0xFFFFFFFFu, kClsStatic = 0xFFFFFFFEu;
+constexpr int kStillMin = 16;       // shortest stay (steps inside the chunk) that becomes a static-array entry
+constexpr int kSplitMaxChunk = 240;  // `since` has 8 bits
+constexpr int kSplitDefaultChunk = 240;
+// a static-array entry {xy, agent, state word | since << 16, until} is a candidate at row `row` (step t) iff
+__device__ __forceinline__ bool entry_valid(const int4& e, int row, int t) { return ((e.z >> 16) & 0xff) <= row + 1 && t < e.w; }
+// steps of [tb, tb + S) at which an agent standing in the zero-velocity segment [t0, next_t0) is unchanged
+__device__ __forceinline__ int still_len(int t0, int next_t0, int tb, int S) { return min(next_t0, tb + S) - max(t0 + 1, tb); }
 constexpr int kDynCellMul = 4;
 
 #define OVF_PAIR 1ULL
@@ -299,8 +317,10 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
     // the split pipeline's rows say "not around" instead, so that its scatter needs no window
     if (win.x > t_first + min(r0 + kRowsPerThread, rows) || win.y <= t_first + r0) {
       if (coarse)
-        for (int row = r0; row < min(r0 + kRowsPerThread, rows); ++row)
+        for (int row = r0; row < min(r0 + kRowsPerThread, rows); ++row) {
           p.rec[(size_t)row * p.N + slot] = make_int4(0, 0, pack_fl(-1, -1), 0);
+          if (row >= 1) p.dmask[(size_t)(row - 1) * p.N + slot] = 0;
+        }
       return;
     }
   }
@@ -328,11 +348,13 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
   for (int rg = r0; rg < row_end; rg += kGroup) {
     int4 out[kGroup];
     int cellv[kGroup];  // >= 0: cell to take a rank in; -1: store as is; -2: no store
+    bool live[kGroup];  // a row of the chunk
 #pragma unroll
     for (int k = 0; k < kGroup; ++k) {
       const int row = rg + k;
       cellv[k] = -2;
-      if (row >= row_end) continue;
+      live[k] = row < row_end;
+      if (!live[k]) continue;
       t = t_first + row;
       while (t >= next_t0) {
         ++c;
@@ -364,14 +386,26 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
       const FloorDev& fd = p.floors[f];
       const int32_t xy = (x - fd.minx) | ((y - fd.miny) << 16);
       out[k] = make_int4(xy, still ? next_t0 : t + 1, pack_fl(f, loc, changed, still ? 0 : 1), 0);
-      if (do_bin && row >= 1) cellv[k] = coarse ? dcell_of_xy(p, fd, xy) : cell_of_xy(p, fd, xy);
+      if (do_bin && row >= 1) {
+        if (!coarse) {
+          cellv[k] = cell_of_xy(p, fd, xy);
+        } else if (!changed && still_len(s.x & 0xffffff, next_t0, p.chunk_begin, p.chunk_steps) >= p.still_min) {
+          // inside a stay that k_classify entered into the static array: not binned at this step; the
+          // record itself is needed only as the previous-step record of the stay's last step + 1
+          cellv[k] = (t + 1 >= next_t0) ? -1 : -3;
+        } else {
+          cellv[k] = dcell_of_xy(p, fd, xy);
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < kGroup; ++k)
       if (cellv[k] >= 0) out[k].w = (int)atomicAdd(&p.cells[(size_t)(rg + k - 1) * stride + cellv[k]], 1u);
 #pragma unroll
-    for (int k = 0; k < kGroup; ++k)
-      if (cellv[k] != -2) p.rec[(size_t)(rg + k) * p.N + slot] = out[k];
+    for (int k = 0; k < kGroup; ++k) {
+      if (cellv[k] > -2) p.rec[(size_t)(rg + k) * p.N + slot] = out[k];
+      if (coarse && live[k] && rg + k >= 1) p.dmask[(size_t)(rg + k - 1) * p.N + slot] = cellv[k] >= 0;
+    }
   }
 }
 
@@ -390,6 +424,7 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
 __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t c = kClsOut;
+  uint32_t need = 0;
   bool dyn = false;
   if (a < p.N) {
     const int2 win = p.window[a];
@@ -428,20 +463,59 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
         next_t0 = (lo < se) ? (__ldg(&p.segs[lo].x) & 0xffffff) : INT_MAX;
       }
       p.seg_cur[a] = (uint32_t)(lo - sb);
-      const long long ci = lo - 1;
+      long long ci = lo - 1;
       dyn = true;
-      if (ci >= sb && t >= 0) {
-        if (s.w == 0 && next_t0 >= tb + S) {
-          dyn = false;
-          const int f = (s.x >> 24) & 0xff;
-          const int loc = (f < p.F) ? lut_lookup(p.floors[f], s.y, s.z) : -1;
-          if (loc >= 0) {
-            const FloorDev& fd = p.floors[f];
-            const int32_t xy = (s.y - fd.minx) | ((s.z - fd.miny) << 16);
-            const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
-            p.srec[a] = make_int4(xy, next_t0, pack_fl(f, loc, 0, 0), (int)rk);
-            c = kClsStatic;
+      if (ci >= sb && t >= 0 && s.w == 0 && next_t0 >= tb + S) {
+        dyn = false;
+        const int f = (s.x >> 24) & 0xff;
+        const int loc = (f < p.F) ? lut_lookup(p.floors[f], s.y, s.z) : -1;
+        if (loc >= 0) {
+          const FloorDev& fd = p.floors[f];
+          const int32_t xy = (s.y - fd.minx) | ((s.z - fd.miny) << 16);
+          const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
+          p.srec[a] = make_int4(xy, next_t0, pack_fl(f, loc, 0, 0), (int)rk);
+          c = kClsStatic;
+        }
+      }
+      if (dyn) {
+        // the agent's stays of >= kStillMin steps inside the chunk become entries of the static array
+        // (k_expand_dyn applies the same rule, still_len, to leave those steps out of the per-step arrays);
+        // row groups (8 rows; row = step - (tb - 1)) that lie inside such a stay, or outside the agent's
+        // window, are dropped from `need`: no kernel touches them
+        need = 0xffffffffu;
+        {
+          // rows with step + 1 < win.x or step >= win.y carry nothing
+          const int r_lo = win.x - 1 - (tb - 1), r_hi = (win.y == INT_MAX) ? INT_MAX : win.y - (tb - 1);  // rows [r_lo, r_hi) matter
+          for (int g = 0; g < 32; ++g)
+            if (8 * g + 7 < r_lo || 8 * g >= r_hi) need &= ~(1u << g);
+        }
+        if (ci < sb) { ci = sb; if (ci < se) { s = __ldg(&p.segs[ci]); next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX; } }
+        while (ci < se) {
+          const int t0 = s.x & 0xffffff;
+          if (t0 >= tb + S) break;
+          if (s.w == 0 && still_len(t0, next_t0, tb, S) >= p.still_min) {
+            const int f = (s.x >> 24) & 0xff;
+            const int loc = (f < p.F) ? lut_lookup(p.floors[f], s.y, s.z) : -1;
+            if (loc >= 0) {
+              const FloorDev& fd = p.floors[f];
+              const int32_t xy = (s.y - fd.minx) | ((s.z - fd.miny) << 16);
+              const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
+              const uint32_t e = atomicAdd(p.ient_count, 1u);
+              const int since = max(t0 + 1, tb) - (tb - 1);
+              p.ient[e] = make_int4(xy, a, pack_fl(f, loc, 0, 0) | (since << 16), next_t0);
+              p.ient_rank[e] = rk;
+              // covered rows [since, rb); the last one is kept when a step of the chunk follows it (it is
+              // that step's previous record)
+              const int rb = min(next_t0, tb + S) - (tb - 1);
+              const int keep_from = (next_t0 < tb + S) ? rb - 1 : rb;
+              for (int g = (since + 7) >> 3; 8 * g + 7 < keep_from; ++g) need &= ~(1u << g);
+            }
           }
+          if (next_t0 >= tb + S) break;
+          ++ci;
+          if (ci >= se) break;
+          s = __ldg(&p.segs[ci]);
+          next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
         }
       }
     }
@@ -455,6 +529,7 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
     if (dyn) {
       c = base + __popc(m & ((1u << lane) - 1u));
       p.dyn_agent[c] = (uint32_t)a;
+      p.need[c] = need;
     }
   }
   if (a < p.N) p.cls[a] = c;
@@ -462,10 +537,18 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
 
 __global__ void __launch_bounds__(256) k_scatter_static(Params p) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= p.N || p.cls[a] != kClsStatic) return;
-  const int4 r = p.srec[a];
-  const uint32_t dest = p.scells[cell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
-  p.ssorted[dest] = make_int4(r.x, a, r.z, r.y);
+  if (a < p.N && p.cls[a] == kClsStatic) {
+    const int4 r = p.srec[a];
+    const uint32_t dest = p.scells[cell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
+    p.ssorted[dest] = make_int4(r.x, a, r.z, r.y);
+  }
+  // the dynamic agents' stays
+  const uint32_t ne = *p.ient_count;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+    const int4 r = p.ient[e];
+    const uint32_t dest = p.scells[cell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + p.ient_rank[e];
+    p.ssorted[dest] = r;
+  }
 }
 
 // expansion of the dynamic agents only: work item = (row group, dynamic index), grid-stride
@@ -475,6 +558,7 @@ __global__ void __launch_bounds__(128) k_expand_dyn(Params p, int t_first, int r
   for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < Dn * groups;
        w += (unsigned long long)gridDim.x * blockDim.x) {
     const uint32_t g = (uint32_t)(w / Dn), j = (uint32_t)(w - (unsigned long long)g * Dn);
+    if (!((p.need[j] >> g) & 1u)) continue;  // kRowsPerThread == 8: g is the row group of `need`
     expand_rows(p, (int)p.dyn_agent[j], (size_t)j, t_first, rows, (int)g * kRowsPerThread, 1, kRowsPerThread, true);
   }
 }
@@ -486,9 +570,11 @@ __global__ void __launch_bounds__(256) k_scatter_dyn(Params p, int rows /* S */)
   const int4* rec = p.rec + (size_t)(row + 1) * p.N;
   const uint32_t* cs = p.cells + (size_t)row * p.dcells_stride;
   int4* out = p.sorted + (size_t)row * p.N;
+  const uint8_t* mask = p.dmask + (size_t)row * p.N;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < Dn; j += gridDim.x * blockDim.x) {
-    const int4 r = rec[j];  // every row of a dynamic agent is written ("not around" outside its window)
-    if (!fl_located(r.z)) continue;
+    // not around, in no space, or inside a stay that is in the static array
+    if (!((p.need[j] >> ((row + 1) >> 3)) & 1u) || !mask[j]) continue;
+    const int4 r = rec[j];
     const uint32_t dest = cs[dcell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
     out[dest] = make_int4(r.x, (int)p.dyn_agent[j], r.z, r.y);
   }
@@ -954,8 +1040,11 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
   if (s_void) return;
   int4 me = make_int4(0, 0, 0, 0);
   int qa = 0, qa_end = 0, qb = 0, qb_end = 0, f = 0, loc = -1;
+  bool me_ok = q0 < total;
   if (q0 < total) {
     me = srt[q0];
+    // the static array also holds stays that begin later in the chunk: only those holding at this step
+    if (statics) me_ok = entry_valid(me, row, t_begin + row);
     f = fl_floor(me.z); loc = fl_loc(me.z);
     const FloorDev& fd = p.floors[f];
     int cx = div_cell(p, xy_x(me.x)), cy = div_cell(p, xy_y(me.x));
@@ -979,7 +1068,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
     __syncthreads();
   }
   unsigned long long tests = 0, hits = 0, runs = 0;
-  if (q0 < total) {
+  if (me_ok) {
     const FloorDev& fd = p.floors[f];
     const uint32_t t = (uint32_t)(t_begin + row);
     const int sub = (blockIdx.x + blockIdx.y) & (kSubBuffers - 1);
@@ -988,6 +1077,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pairs(Params p, int t_begin, i
       const int qs = rg ? qb : qa, qe = rg ? qb_end : qa_end;
       for (int q = qs; q < qe; ++q) {
         int4 ot = staged ? win[q - w0] : srt[q];
+        if (statics && !entry_valid(ot, row, (int)t)) continue;
         ++tests;
         if (within_xy(me.x, ot.x, p) && loc_rule_ordered(fd, me.y, loc, ot.y, fl_loc(ot.z))) {
           uint32_t run = aggregate ? run_length(p, me.w, ot.w, t) : 1u;
@@ -1182,8 +1272,8 @@ struct HitQueue {
   uint16_t who[64];  // the changed agent's index in the batch
 };
 
-__device__ __forceinline__ void drain_hits(const Params& p, HitQueue& q, const int4* s_me, int count, uint32_t t, int sub,
-                                           unsigned long long& hits, unsigned long long& runs) {
+__device__ __forceinline__ void drain_hits(const Params& p, HitQueue& q, const int4* s_me, const int4* s_prev, int count,
+                                           uint32_t t, int sub, unsigned long long& hits, unsigned long long& runs) {
   const int lane = threadIdx.x & 31;
   bool good = false;
   ContactRec rec;
@@ -1200,8 +1290,18 @@ __device__ __forceinline__ void drain_hits(const Params& p, HitQueue& q, const i
       ++runs;
       rec.a1 = (uint32_t)min(me.y, ot.y); rec.a2 = (uint32_t)max(me.y, ot.y);
       rec.t_run = (t - (uint32_t)p.chunk_begin) | ((run - 1u) << 12);
-      rec.bucket = (((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
-                     (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu) | 0x40000000u;
+      rec.bucket = ((uint32_t)fd.hist_base + (uint32_t)(xy_y(me.x) + xy_y(ot.x)) * (uint32_t)fd.hist_w +
+                    (uint32_t)(xy_x(me.x) + xy_x(ot.x))) & 0x3fffffffu;
+      // Was the pair in contact one step earlier (does the event continue)?  A candidate that is
+      // exactly where and what it was a step ago (static, or standing: `changed` clear) IS its own
+      // previous record, and the changed agent's previous record was fetched once in phase 1: decided
+      // here, k_accumulate reads no records for it.  Two changed agents: left to k_accumulate (bit 30).
+      if (!fl_changed(ot.z)) {
+        const int4 mp = s_prev[q.who[lane]];
+        const bool was = me.y < ot.y ? contact_eval(p, mp, ot) : contact_eval(p, ot, mp);  // (lower id, higher id), as k_accumulate does
+        rec.bucket |= was ? 0x80000000u : 0u;
+      }
+      else rec.bucket |= 0x40000000u;
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, good);
@@ -1217,7 +1317,7 @@ __device__ __forceinline__ void drain_hits(const Params& p, HitQueue& q, const i
     }
   }
   if (good && !stored) {  // no contact buffer, or it is full (k_accumulate clamps the count): apply here
-    const bool was = contact_prev(p, rec.t_run & 0xfffu, rec.a1, rec.a2);
+    const bool was = (rec.bucket & 0x40000000u) ? contact_prev(p, rec.t_run & 0xfffu, rec.a1, rec.a2) : (rec.bucket >> 31) != 0;
     const uint32_t first = (!was || (int32_t)t == p.range_begin) ? t : NO_STEP;
     pair_upsert(p, rec.a1, rec.a2, first, run, was ? 0u : 1u);
     coord_upsert_rel(p, fl_floor(me.z), xy_x(me.x) + xy_x(ot.x), xy_y(me.x) + xy_y(ot.x), (unsigned long long)run);
@@ -1227,6 +1327,7 @@ __device__ __forceinline__ void drain_hits(const Params& p, HitQueue& q, const i
 template <int kPS>
 __global__ void __launch_bounds__(kPS, 1024 / kPS) k_pairs_changed_split(Params p, int t_begin, int rows /* S */, int all_row) {
   __shared__ int4 s_me[kPS];
+  __shared__ int4 s_prev[kPS];  // the batch's agents one step earlier
   __shared__ HitQueue s_queue[kPS / 32];
   __shared__ int s_delta[kPS * 6];        // candidate position = flat index + s_delta[agent * 6 + range]
   __shared__ uint16_t s_owner[kTile];     // agent * 6 + range of a flat index (relative to the tile)
@@ -1283,6 +1384,7 @@ __global__ void __launch_bounds__(kPS, 1024 / kPS) k_pairs_changed_split(Params 
         len[5] = up ? (int)cd[rbu + x1 + 1] - qs[5] : 0;
       }
       s_me[threadIdx.x] = me;
+      s_prev[threadIdx.x] = p.rec[(size_t)row * p.N + p.cls[me.y]];  // row `row` holds step t-1 (row 0: the halo step)
 #pragma unroll
       for (int r = 0; r < 6; ++r) total += len[r];
     }
@@ -1331,8 +1433,10 @@ __global__ void __launch_bounds__(kPS, 1024 / kPS) k_pairs_changed_split(Params 
           const bool dyn_cand = o - i * 6 >= 3;
           ot = __ldg((dyn_cand ? srt : p.ssorted) + (tile + pp + s_delta[o]));
           const int4 me = s_me[i];
-          // a dynamic candidate: not the agent itself, and not a pair the other agent owns
-          const bool skip = dyn_cand && (ot.y == me.y || ((all || fl_changed(ot.z)) && ot.y < me.y));
+          // a dynamic candidate: not the agent itself, and not a pair the other agent owns;
+          // a static-array candidate: a stay that holds at this step
+          const bool skip = dyn_cand ? (ot.y == me.y || ((all || fl_changed(ot.z)) && ot.y < me.y))
+                                     : !entry_valid(ot, row, (int)t);
           if (!skip) {
             ++tests;
             hit = within_xy(me.x, ot.x, p);
@@ -1348,7 +1452,7 @@ __global__ void __launch_bounds__(kPS, 1024 / kPS) k_pairs_changed_split(Params 
           qn += __popc(m);
           __syncwarp();
           if (qn >= 32) {
-            drain_hits(p, queue, s_me, 32, t, sub, hits, runs);
+            drain_hits(p, queue, s_me, s_prev, 32, t, sub, hits, runs);
             __syncwarp();
             int4 mv = make_int4(0, 0, 0, 0);
             uint16_t mw = 0;
@@ -1364,7 +1468,7 @@ __global__ void __launch_bounds__(kPS, 1024 / kPS) k_pairs_changed_split(Params 
     }
     // the batch's agents (s_me) are replaced next: finish what is queued
     if (qn) {
-      drain_hits(p, queue, s_me, qn, t, sub, hits, runs);
+      drain_hits(p, queue, s_me, s_prev, qn, t, sub, hits, runs);
       qn = 0;
     }
     __syncthreads();  // the batch's shared arrays are reused
@@ -1889,6 +1993,12 @@ struct citam_engine {
   uint32_t* cls_buf[2] = {nullptr, nullptr};
   int4* ssorted = nullptr;
   uint32_t *scells = nullptr, *dyn_agent = nullptr, *dyn_count = nullptr, *seg_cur = nullptr;
+  int4* ient = nullptr;
+  uint32_t *ient_rank = nullptr, *ient_count = nullptr;
+  uint8_t* dmask = nullptr;
+  uint32_t* need = nullptr;
+  int chunk_steps = 0;
+  int still_min = kStillMin;  // CITAM_STILL_MIN (>= kStillMin; e.g. 100000 keeps every dynamic agent in the per-step arrays)
   int dtotal_cells = 0, dcells_stride = 4;
   bool split = false;  // the chunk being processed uses the split pipeline
   bool no_fast_stats = false;  // CITAM_NO_FAST_STATS=1: statistics always from the pass over the pair table (tests)
@@ -2049,6 +2159,8 @@ static Params make_params(citam_engine* e) {
   if (e->split) {
     p.cls = e->cls_buf[e->cur]; p.srec = e->srec_buf[e->cur];
     p.ssorted = e->ssorted; p.scells = e->scells; p.dyn_agent = e->dyn_agent; p.dyn_count = e->dyn_count; p.seg_cur = e->seg_cur;
+    p.ient = e->ient; p.ient_rank = e->ient_rank; p.ient_count = e->ient_count; p.dmask = e->dmask; p.need = e->need;
+    p.chunk_steps = e->chunk_steps; p.still_min = e->still_min;
   }
   p.ctr = e->ctr_d;
   return p;
@@ -2064,7 +2176,9 @@ static void free_chunk(citam_engine* e) {
   e->chg_list = e->chg_count = e->part_sums = nullptr;
   for (int b = 0; b < 2; ++b) { cudaFree(e->srec_buf[b]); cudaFree(e->cls_buf[b]); e->srec_buf[b] = nullptr; e->cls_buf[b] = nullptr; }
   cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count); cudaFree(e->seg_cur);
+  cudaFree(e->ient); cudaFree(e->ient_rank); cudaFree(e->ient_count); cudaFree(e->dmask); cudaFree(e->need);
   e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = e->seg_cur = nullptr;
+  e->ient = nullptr; e->ient_rank = e->ient_count = e->need = nullptr; e->dmask = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -2145,7 +2259,15 @@ static int ensure_ready(citam_engine* e, int want_steps) {
     CK(cudaMalloc(&e->srec_buf[b], sizeof(int4) * n));
     CK(cudaMalloc(&e->cls_buf[b], sizeof(uint32_t) * n));
   }
-  CK(cudaMalloc(&e->ssorted, sizeof(int4) * n));
+  // the static array: one entry per agent standing through the chunk, plus the dynamic agents' stays
+  // (disjoint, >= kStillMin steps each: at most S / kStillMin per agent)
+  const size_t n_stays = (e->log_cap == 0 && !e->no_split) ? n * (size_t)(std::min(S, kSplitMaxChunk) / kStillMin + 1) : 1;
+  CK(cudaMalloc(&e->ssorted, sizeof(int4) * std::max(n, n_stays)));
+  CK(cudaMalloc(&e->ient, sizeof(int4) * n_stays));
+  CK(cudaMalloc(&e->ient_rank, sizeof(uint32_t) * n_stays));
+  CK(cudaMalloc(&e->ient_count, sizeof(uint32_t)));
+  CK(cudaMalloc(&e->need, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->dmask, (e->log_cap == 0 && !e->no_split) ? n * (size_t)S : 1));
   CK(cudaMalloc(&e->scells, sizeof(uint32_t) * (size_t)e->cells_stride));
   CK(cudaMalloc(&e->dyn_agent, sizeof(uint32_t) * n));
   CK(cudaMalloc(&e->dyn_count, sizeof(uint32_t)));
@@ -2156,7 +2278,8 @@ static int ensure_ready(citam_engine* e, int want_steps) {
 }
 
 static int pick_chunk(citam_engine* e, int steps) {
-  if (e->cfg.steps_per_chunk > 0) return std::min(std::min(steps, e->cfg.steps_per_chunk), kMaxChunk);
+  const bool split_mode = e->log_cap == 0 && !e->no_split;
+  if (e->cfg.steps_per_chunk > 0) return std::min(std::min(steps, e->cfg.steps_per_chunk), split_mode ? kSplitMaxChunk : kMaxChunk);
   // ~64M agent-steps per launch group (3.3 GiB of per-step records), bounded by 1 GiB of histogram rows
   const bool split = e->log_cap == 0 && !e->no_split;
   long long by_agents = std::max(1LL, ((split ? 256LL : 64LL) << 20) / std::max(1, e->N));
@@ -2164,7 +2287,7 @@ static int pick_chunk(citam_engine* e, int steps) {
   long long s = std::min(by_agents, by_cells);
   // without the contact log (split pipeline) an agent is binned once per chunk if it stands still for
   // the whole chunk: short chunks keep most agents in that class
-  s = std::min<long long>(s, e->log_cap == 0 ? 128 : kMaxChunk);
+  s = std::min<long long>(s, e->log_cap == 0 ? kSplitDefaultChunk : kMaxChunk);
   s = std::max<long long>(s, 1);
   return (int)std::min<long long>(s, steps);
 }
@@ -2247,9 +2370,11 @@ static int run_sorted_stages(citam_engine* e, int t_begin, int rows) {
 // step.  Only a range's first step looks at static-static pairs (k_pairs on the static array): at every
 // other step such a pair is inside a run that an earlier step added in one piece.
 static int run_split_chunk(citam_engine* e, int tb, int steps) {
+  e->chunk_steps = steps;
   Params p = make_params(e);
   p.chunk_begin = tb;
   const int rows = steps + 1;  // + halo row for step tb-1
+  CK(cudaMemsetAsync(e->ient_count, 0, sizeof(uint32_t), e->stream));
   CK(cudaMemsetAsync(e->scells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
   CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->dcells_stride * steps, e->stream));
   CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
@@ -2275,7 +2400,9 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
   {
     Timed tm(e, CITAM_K_PAIRS);
     if (first) {
-      k_pairs<<<dim3(gN, 1), 256, 0, e->stream>>>(p, tb, 1, 1, 1);
+      // the static array holds up to steps / kStillMin + 1 entries per agent (blocks past its end return at once)
+      const unsigned gS = (unsigned)(((size_t)e->N * (size_t)(steps / kStillMin + 1) + 255) / 256);
+      k_pairs<<<dim3(gS, 1), 256, 0, e->stream>>>(p, tb, 1, 1, 1);
       e->launches++;
     }
     if (e->pair_tpb == 128) k_pairs_changed_split<128><<<dim3(128, steps), 128, 0, e->stream>>>(p, tb, steps, first ? 0 : -1);
@@ -2369,6 +2496,7 @@ static int create_impl(citam_engine* e, const citam_config* cfg) {
   if (const char* g = getenv("CITAM_ACC_BLOCKS")) e->acc_blocks = std::max(1, atoi(g));
   if (const char* g = getenv("CITAM_ACC_ILP")) e->acc_ilp = atoi(g);
   if (const char* g = getenv("CITAM_PAIR_TPB")) e->pair_tpb = atoi(g);
+  if (const char* g = getenv("CITAM_STILL_MIN")) e->still_min = std::max(kStillMin, atoi(g));
   if (const char* g = getenv("CITAM_NO_SPLIT")) e->no_split = atoi(g) != 0;
   if (const char* g = getenv("CITAM_NO_FAST_STATS")) e->no_fast_stats = atoi(g) != 0;
   e->cfg = *cfg;
@@ -2405,6 +2533,23 @@ static int create_impl(citam_engine* e, const citam_config* cfg) {
   for (int b = 0; b < 2; ++b) {
     CK(cudaEventCreateWithFlags(&e->ev_built[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_applied[b], cudaEventDisableTiming));
+  }
+  if (const char* g = getenv("CITAM_L2_PERSIST")) {
+    // experiment (profiles/README.md): pin the per-agent counter words (2 reductions per applied record)
+    // in the persisting part of L2 for the accumulation stream
+    if (atoi(g) != 0) {
+      cudaDeviceProp prop;
+      CK(cudaGetDeviceProperties(&prop, e->device));
+      size_t bytes = std::min<size_t>(sizeof(unsigned long long) * n, (size_t)prop.accessPolicyMaxWindowSize);
+      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize)));
+      cudaStreamAttrValue v{};
+      v.accessPolicyWindow.base_ptr = e->agent_dur;
+      v.accessPolicyWindow.num_bytes = bytes;
+      v.accessPolicyWindow.hitRatio = 1.0f;
+      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      CK(cudaStreamSetAttribute(e->stream2, cudaStreamAttributeAccessPolicyWindow, &v));
+    }
   }
   {
     int bad = 1;
