@@ -298,11 +298,14 @@ def run_reference(args):
     g, threads = cpu_oracle(fac, seg_off, segs, p, D)
     T = p["total_timesteps"]
     block = args.block or auto_block(p)
-    per = 32 if p["n_agents"] <= 100_000 else 8  # simulation steps per thread and bench step (+ a one-step halo each)
+    # simulation steps per thread and bench step (+ a one-step halo each): 32, or as many (>= 4) as keep the
+    # whole --steps K run within ~150 s of CPU time, judged from a short warm-up sample
+    probe = max(2, 4 * threads)
+    u0, d0 = time_cpu_sample(g, threads, block_starts(T, probe, 1, 0, 1, offset=7), probe)
+    rate = u0 / max(d0, 1e-6)
+    per = int(max(4, min(32, 150.0 * rate / (max(1, args.steps) * g.n_agents * threads))))
     steps_each = max(2, per * threads)
-    starts_w = block_starts(T, steps_each, max(1, args.warmup), 0, 1, offset=7)
     starts = block_starts(T, steps_each, args.steps, 0, 1)
-    time_cpu_sample(g, threads, starts_w[: max(1, min(args.warmup, 1))], steps_each)
     units, dt = time_cpu_sample(g, threads, starts, steps_each)
     v = units / dt
     sample = "%d samples x %d simulation steps x %d agents (%d steps per thread + halo), spread over the day" % (
@@ -520,7 +523,7 @@ def run_b200(args):
         b = tm0.get(k, {"ms": 0.0, "launches": 0})
         if v["launches"] > b["launches"]:
             kern[k] = {"ms": v["ms"] - b["ms"], "launches": v["launches"] - b["launches"]}
-    step_kinds = [k for k in kern if k in ("expand_bin", "scan", "scatter", "pairs", "accumulate")]
+    step_kinds = [k for k in kern if k in ("classify", "expand_bin", "scan", "scatter", "pairs", "accumulate")]
     dom = max(step_kinds, key=lambda k: kern[k]["ms"]) if step_kinds else None
     # k_accumulate is the HBM-bound kernel of the step (random read-modify-writes); the detection kernel
     # that ties with it is bound by instruction issue.  The roofline line describes k_accumulate whenever
@@ -562,6 +565,27 @@ def run_b200(args):
             "whole_step_achieved": alg_updates / (run_ms * 1e-3) / 1e9, "whole_step_frac": alg_updates / (run_ms * 1e-3) / 1e9 / peak,
             "whole_step_survey_rule_frac": alg_survey / (run_ms * 1e-3) / 1e9 / peak,
         }
+
+    if roof and roof["kernel"] == "accumulate" and world == 1:
+        # what the memory system sustains for this access pattern: random 16-byte probe + 8-byte reduction
+        # over a table of the pair table's size, nothing else (citam_measure_random_updates)
+        try:
+            from citam_b200.engine import measure_random_updates
+
+            mups = measure_random_updates(pair_cap * 16, 1 << 28, True, device=local)
+            per_record = 1.0  # the pair-table update (17 GB, no locality); the histogram one is counted as free
+            rec_rate = runs / (kern["accumulate"]["ms"] * 1e-3) / 1e6
+            roof["random_update_ceiling"] = {
+                "million_updates_per_s": mups, "table_bytes": int(pair_cap * 16),
+                "k_accumulate_million_records_per_s": rec_rate,
+                "k_accumulate_million_updates_per_s": rec_rate * per_record,
+                "frac_of_ceiling": rec_rate * per_record / mups,
+                "what": "2^28 random (16-byte load + 8-byte reduction) updates, four in flight per thread, over a zeroed table "
+                        "of the pair table's size; k_accumulate makes one such update per record (pair slot), one more over the "
+                        "0.46 GB histogram and two L2-resident ones: the fraction counts the pair-table update alone",
+            }
+        except Exception as e:  # measurement aid only
+            roof["random_update_ceiling"] = {"error": str(e)[:200]}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------
     e2e = None
@@ -605,11 +629,18 @@ def run_b200(args):
             buf = torch.empty((max(1, n_pairs), 3), dtype=torch.int64, device="cuda")
             barrier()
             ev[0].record()
+            got = eng.export_pairs_device(buf.data_ptr(), n_pairs)  # first call: allocates the sort's ping-pong buffers
+            ev[1].record()
+            barrier()
+            first_ms = ev[0].elapsed_time(ev[1])
+            ev[0].record()
             got = eng.export_pairs_device(buf.data_ptr(), n_pairs)
             ev[1].record()
             torch.cuda.synchronize()
-            fin = {"finalize_ms": max_over_ranks(ev[0].elapsed_time(ev[1])), "pairs_sorted_on_this_rank": int(got),
-                   "what": "compaction of the pair table + device radix sort by (first contact step, a1, a2) into a device buffer"}
+            fin = {"finalize_ms": max_over_ranks(ev[0].elapsed_time(ev[1])), "finalize_first_call_ms": max_over_ranks(first_ms),
+                   "pairs_sorted_on_this_rank": int(got),
+                   "what": "compaction of the pair table + device radix sort by (first contact step, a1, a2) into a device buffer; "
+                           "the first call also allocates the sort's buffers (cudaMalloc of 2 x 16 B x pairs)"}
             fin["sorted_ok"] = rows_sorted(buf, int(got))
             if world == 1 and not args.no_e2e and got * 24 < 48e9:
                 host = torch.empty((max(1, got), 3), dtype=torch.int64).pin_memory()

@@ -16,8 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libcitam_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
 FLAG_TIMING = 1
 FLAG_HASHED_COORDS = 2
-N_KERNELS = 8
-KERNEL_NAMES = ["expand_bin", "scan", "scatter", "pairs", "lut", "finalize", "misc", "accumulate"]
+N_KERNELS = 9
+KERNEL_NAMES = ["expand_bin", "scan", "scatter", "pairs", "lut", "finalize", "misc", "accumulate", "classify"]
 
 
 class CitamDeviceError(RuntimeError):
@@ -98,7 +98,7 @@ EXPORTS = [
     "citam_get_timings", "citam_agent_durations_device", "citam_merge_pairs", "citam_merge_coords",
     "citam_hist_device", "citam_export_pairs_device", "citam_export_coords_device", "citam_partition_pairs_device",
     "citam_clear_pairs", "citam_merge_pairs_device", "citam_statistics_begin", "citam_stats_arrays_device",
-    "citam_statistics_end", "citam_statistics_counters",
+    "citam_statistics_end", "citam_statistics_counters", "citam_measure_random_updates",
 ]
 ABI_VERSION = 3
 
@@ -158,6 +158,7 @@ def load() -> C.CDLL:
         "citam_stats_arrays_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), pu64]),
         "citam_statistics_end": (C.c_int, [vp, C.POINTER(Stats)]),
         "citam_statistics_counters": (C.c_int, [vp, C.POINTER(Stats)]),
+        "citam_measure_random_updates": (C.c_int, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -189,6 +189,8 @@ struct Params {
   uint8_t* dmask;           // [S][N] by dynamic index: 1 = the agent is binned at this step
   uint32_t* need;           // [N] by dynamic index: bit g = rows 8g .. 8g+7 of the chunk hold a step at which the agent
                             // is binned, or the record before one (all other row groups are skipped by every kernel)
+  uint32_t* work;           // [32][N] per row group: the dynamic indices with that bit set
+  uint32_t* work_count;     // [32]
   int32_t chunk_steps;      // steps of the chunk being processed
   int32_t still_min;        // shortest stay that becomes an entry (>= kStillMin; larger than a chunk: none does)
   DevCounters* ctr;
@@ -424,7 +426,6 @@ __global__ void __launch_bounds__(128) k_expand_bin(Params p, int t_first, int r
 __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t c = kClsOut;
-  uint32_t need = 0;
   bool dyn = false;
   if (a < p.N) {
     const int2 win = p.window[a];
@@ -477,47 +478,6 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
           c = kClsStatic;
         }
       }
-      if (dyn) {
-        // the agent's stays of >= kStillMin steps inside the chunk become entries of the static array
-        // (k_expand_dyn applies the same rule, still_len, to leave those steps out of the per-step arrays);
-        // row groups (8 rows; row = step - (tb - 1)) that lie inside such a stay, or outside the agent's
-        // window, are dropped from `need`: no kernel touches them
-        need = 0xffffffffu;
-        {
-          // rows with step + 1 < win.x or step >= win.y carry nothing
-          const int r_lo = win.x - 1 - (tb - 1), r_hi = (win.y == INT_MAX) ? INT_MAX : win.y - (tb - 1);  // rows [r_lo, r_hi) matter
-          for (int g = 0; g < 32; ++g)
-            if (8 * g + 7 < r_lo || 8 * g >= r_hi) need &= ~(1u << g);
-        }
-        if (ci < sb) { ci = sb; if (ci < se) { s = __ldg(&p.segs[ci]); next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX; } }
-        while (ci < se) {
-          const int t0 = s.x & 0xffffff;
-          if (t0 >= tb + S) break;
-          if (s.w == 0 && still_len(t0, next_t0, tb, S) >= p.still_min) {
-            const int f = (s.x >> 24) & 0xff;
-            const int loc = (f < p.F) ? lut_lookup(p.floors[f], s.y, s.z) : -1;
-            if (loc >= 0) {
-              const FloorDev& fd = p.floors[f];
-              const int32_t xy = (s.y - fd.minx) | ((s.z - fd.miny) << 16);
-              const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
-              const uint32_t e = atomicAdd(p.ient_count, 1u);
-              const int since = max(t0 + 1, tb) - (tb - 1);
-              p.ient[e] = make_int4(xy, a, pack_fl(f, loc, 0, 0) | (since << 16), next_t0);
-              p.ient_rank[e] = rk;
-              // covered rows [since, rb); the last one is kept when a step of the chunk follows it (it is
-              // that step's previous record)
-              const int rb = min(next_t0, tb + S) - (tb - 1);
-              const int keep_from = (next_t0 < tb + S) ? rb - 1 : rb;
-              for (int g = (since + 7) >> 3; 8 * g + 7 < keep_from; ++g) need &= ~(1u << g);
-            }
-          }
-          if (next_t0 >= tb + S) break;
-          ++ci;
-          if (ci >= se) break;
-          s = __ldg(&p.segs[ci]);
-          next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
-        }
-      }
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, dyn);
@@ -529,10 +489,83 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
     if (dyn) {
       c = base + __popc(m & ((1u << lane) - 1u));
       p.dyn_agent[c] = (uint32_t)a;
-      p.need[c] = need;
     }
   }
   if (a < p.N) p.cls[a] = c;
+}
+
+// Second half of the classification, one thread per DYNAMIC agent (dense): its stays of >= still_min
+// steps inside the chunk become entries of the static array (k_expand_dyn applies the same rule,
+// still_len, to leave those steps out of the per-step arrays); the row groups (8 rows; row = step -
+// (tb - 1)) that hold a step at which the agent is binned, or the record before one, go into `need`
+// and into the per-group work lists that the per-step kernels walk -- a group that lies inside a stay
+// or outside the agent's window is touched by no kernel.
+__global__ void __launch_bounds__(256) k_classify_dyn(Params p, int tb, int S) {
+  const uint32_t Dn = *p.dyn_count;
+  const int groups = (S + 1 + 7) >> 3;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < Dn; j0 += gridDim.x * blockDim.x) {  // whole warps iterate together
+    const uint32_t j = j0 + threadIdx.x;
+    uint32_t need = 0;
+    if (j < Dn) {
+      const int a = (int)p.dyn_agent[j];
+      const int2 win = p.window[a];
+      const long long sb = p.seg_off[a], se = p.seg_off[a + 1];
+      need = groups >= 32 ? 0xffffffffu : (1u << groups) - 1u;
+      {
+        // rows with step + 1 < win.x or step >= win.y carry nothing: rows [r_lo, r_hi) matter
+        const long long r_lo = (long long)win.x - 1 - (tb - 1), r_hi = (win.y == INT_MAX) ? (1LL << 40) : (long long)win.y - (tb - 1);
+        for (int g = 0; g < groups; ++g)
+          if (8 * g + 7 < r_lo || 8 * g >= r_hi) need &= ~(1u << g);
+      }
+      long long ci = sb + (long long)p.seg_cur[a] - 1;  // the segment holding step tb - 1 (k_classify found it)
+      int4 sg = make_int4(0, 0, 0, 0);
+      int next_t0 = INT_MAX;
+      if (ci < sb) ci = sb;
+      if (ci < se) {
+        sg = __ldg(&p.segs[ci]);
+        next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
+      }
+      while (ci < se) {
+        const int t0 = sg.x & 0xffffff;
+        if (t0 >= tb + S) break;
+        if (sg.w == 0 && still_len(t0, next_t0, tb, S) >= p.still_min) {
+          const int f = (sg.x >> 24) & 0xff;
+          const int loc = (f < p.F) ? lut_lookup(p.floors[f], sg.y, sg.z) : -1;
+          if (loc >= 0) {
+            const FloorDev& fd = p.floors[f];
+            const int32_t xy = (sg.y - fd.minx) | ((sg.z - fd.miny) << 16);
+            const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
+            const uint32_t e = atomicAdd(p.ient_count, 1u);
+            const int since = max(t0 + 1, tb) - (tb - 1);
+            p.ient[e] = make_int4(xy, a, pack_fl(f, loc, 0, 0) | (since << 16), next_t0);
+            p.ient_rank[e] = rk;
+            // covered rows [since, rb); the last one is kept when a step of the chunk follows it (it is
+            // that step's previous record)
+            const int rb = min(next_t0, tb + S) - (tb - 1);
+            const int keep_from = (next_t0 < tb + S) ? rb - 1 : rb;
+            for (int g = (since + 7) >> 3; 8 * g + 7 < keep_from; ++g) need &= ~(1u << g);
+          }
+        }
+        if (next_t0 >= tb + S) break;
+        ++ci;
+        if (ci >= se) break;
+        sg = __ldg(&p.segs[ci]);
+        next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
+      }
+      p.need[j] = need;
+    }
+    // per-group work lists: one reservation per warp and group, entries in lane (= dynamic index) order
+    for (int g = 0; g < groups; ++g) {
+      const unsigned m = __ballot_sync(0xffffffffu, (need >> g) & 1u);
+      if (m == 0) continue;
+      uint32_t base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(&p.work_count[g], (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if ((need >> g) & 1u) p.work[(size_t)g * p.N + base + __popc(m & ((1u << lane) - 1u))] = j;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_scatter_static(Params p) {
@@ -551,29 +584,31 @@ __global__ void __launch_bounds__(256) k_scatter_static(Params p) {
   }
 }
 
-// expansion of the dynamic agents only: work item = (row group, dynamic index), grid-stride
-__global__ void __launch_bounds__(128) k_expand_dyn(Params p, int t_first, int rows, int kRowsPerThread) {
-  const uint32_t Dn = *p.dyn_count;
-  const unsigned long long groups = (unsigned)((rows + kRowsPerThread - 1) / kRowsPerThread);
-  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < Dn * groups;
-       w += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint32_t g = (uint32_t)(w / Dn), j = (uint32_t)(w - (unsigned long long)g * Dn);
-    if (!((p.need[j] >> g) & 1u)) continue;  // kRowsPerThread == 8: g is the row group of `need`
-    expand_rows(p, (int)p.dyn_agent[j], (size_t)j, t_first, rows, (int)g * kRowsPerThread, 1, kRowsPerThread, true);
+// expansion of the dynamic agents: work item = an entry of a row group's work list (blockIdx.y = the
+// group of 8 rows), so every lane has rows to expand and neighbouring lanes hold neighbouring agents
+__global__ void __launch_bounds__(128) k_expand_dyn(Params p, int t_first, int rows) {
+  const int g = blockIdx.y;
+  const uint32_t n = p.work_count[g];
+  const uint32_t* list = p.work + (size_t)g * p.N;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t j = list[w];
+    expand_rows(p, (int)p.dyn_agent[j], (size_t)j, t_first, rows, g * 8, 1, 8, true);
   }
 }
 
 __global__ void __launch_bounds__(256) k_scatter_dyn(Params p, int rows /* S */) {
-  const uint32_t Dn = *p.dyn_count;
   const int row = blockIdx.y;
   if (row >= rows) return;
+  const int g = (row + 1) >> 3;  // the row group of record row `row + 1`
+  const uint32_t n = p.work_count[g];
+  const uint32_t* list = p.work + (size_t)g * p.N;
   const int4* rec = p.rec + (size_t)(row + 1) * p.N;
   const uint32_t* cs = p.cells + (size_t)row * p.dcells_stride;
-  int4* out = p.sorted + (size_t)row * p.N;
   const uint8_t* mask = p.dmask + (size_t)row * p.N;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < Dn; j += gridDim.x * blockDim.x) {
-    // not around, in no space, or inside a stay that is in the static array
-    if (!((p.need[j] >> ((row + 1) >> 3)) & 1u) || !mask[j]) continue;
+  int4* out = p.sorted + (size_t)row * p.N;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t j = list[w];
+    if (!mask[j]) continue;  // not around, in no space, or inside a stay that is in the static array
     const int4 r = rec[j];
     const uint32_t dest = cs[dcell_of_xy(p, p.floors[fl_floor(r.z)], r.x)] + (uint32_t)r.w;
     out[dest] = make_int4(r.x, (int)p.dyn_agent[j], r.z, r.y);
@@ -1893,6 +1928,29 @@ __global__ void k_unpack_durations(const unsigned long long* agent_dur, int N, u
   if (a < N) out[a] = agent_dur[a] & kAgentDurMask;
 }
 
+// Measurement aid (citam_measure_random_updates): n random read-modify-writes over a table, nothing
+// else -- the rate the memory system sustains for k_accumulate's access pattern.
+__global__ void __launch_bounds__(256) k_random_updates(unsigned long long* tab, unsigned long long mask, unsigned long long n,
+                                                        int probe_first) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    unsigned long long h[4], add[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // four independent updates in flight per thread
+      h[k] = mix64(i0 + k * stride + 1) & mask;
+      add[k] = 1ULL;
+      if (probe_first && i0 + k * stride < n) {  // 16-byte load of the slot pair, then the reduction on the same sector
+        ulonglong2 v;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(tab + (h[k] & ~1ULL)));
+        add[k] += (v.x == 0xdeadbeefULL);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k * stride < n) atomicAdd(tab + h[k], add[k]);
+  }
+}
+
 // Records of another engine (rank) into this table.  Only the pair table is touched: per-agent
 // contact seconds are reduced separately (all-reduce of the counters), see the header.
 // kMergeIlp records per thread, first probes of all of them in flight together (latency-bound random inserts).
@@ -1996,7 +2054,7 @@ struct citam_engine {
   int4* ient = nullptr;
   uint32_t *ient_rank = nullptr, *ient_count = nullptr;
   uint8_t* dmask = nullptr;
-  uint32_t* need = nullptr;
+  uint32_t *need = nullptr, *work = nullptr, *work_count = nullptr;
   int chunk_steps = 0;
   int still_min = kStillMin;  // CITAM_STILL_MIN (>= kStillMin; e.g. 100000 keeps every dynamic agent in the per-step arrays)
   int dtotal_cells = 0, dcells_stride = 4;
@@ -2025,6 +2083,8 @@ struct citam_engine {
   unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
   unsigned long long* dur_out = nullptr;  // unpacked contact seconds (export scratch)
+  void* sort_buf[2] = {nullptr, nullptr};  // ping-pong buffers of the ordered pair export, kept between calls
+  size_t sort_bytes = 0;                   // (a first cudaMalloc of several GB costs hundreds of ms)
   bool counters_match = true;  // the per-agent counter words describe exactly the pairs in the table
   unsigned long long steps_since_reset = 0;
   DevCounters* ctr_d = nullptr;
@@ -2159,7 +2219,7 @@ static Params make_params(citam_engine* e) {
   if (e->split) {
     p.cls = e->cls_buf[e->cur]; p.srec = e->srec_buf[e->cur];
     p.ssorted = e->ssorted; p.scells = e->scells; p.dyn_agent = e->dyn_agent; p.dyn_count = e->dyn_count; p.seg_cur = e->seg_cur;
-    p.ient = e->ient; p.ient_rank = e->ient_rank; p.ient_count = e->ient_count; p.dmask = e->dmask; p.need = e->need;
+    p.ient = e->ient; p.ient_rank = e->ient_rank; p.ient_count = e->ient_count; p.dmask = e->dmask; p.need = e->need; p.work = e->work; p.work_count = e->work_count;
     p.chunk_steps = e->chunk_steps; p.still_min = e->still_min;
   }
   p.ctr = e->ctr_d;
@@ -2176,9 +2236,9 @@ static void free_chunk(citam_engine* e) {
   e->chg_list = e->chg_count = e->part_sums = nullptr;
   for (int b = 0; b < 2; ++b) { cudaFree(e->srec_buf[b]); cudaFree(e->cls_buf[b]); e->srec_buf[b] = nullptr; e->cls_buf[b] = nullptr; }
   cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count); cudaFree(e->seg_cur);
-  cudaFree(e->ient); cudaFree(e->ient_rank); cudaFree(e->ient_count); cudaFree(e->dmask); cudaFree(e->need);
+  cudaFree(e->ient); cudaFree(e->ient_rank); cudaFree(e->ient_count); cudaFree(e->dmask); cudaFree(e->need); cudaFree(e->work); cudaFree(e->work_count);
   e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = e->seg_cur = nullptr;
-  e->ient = nullptr; e->ient_rank = e->ient_count = e->need = nullptr; e->dmask = nullptr;
+  e->ient = nullptr; e->ient_rank = e->ient_count = e->need = e->work = e->work_count = nullptr; e->dmask = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -2267,6 +2327,8 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->ient_rank, sizeof(uint32_t) * n_stays));
   CK(cudaMalloc(&e->ient_count, sizeof(uint32_t)));
   CK(cudaMalloc(&e->need, sizeof(uint32_t) * n));
+  CK(cudaMalloc(&e->work, (e->log_cap == 0 && !e->no_split) ? sizeof(uint32_t) * n * 32 : 4));
+  CK(cudaMalloc(&e->work_count, sizeof(uint32_t) * 32));
   CK(cudaMalloc(&e->dmask, (e->log_cap == 0 && !e->no_split) ? n * (size_t)S : 1));
   CK(cudaMalloc(&e->scells, sizeof(uint32_t) * (size_t)e->cells_stride));
   CK(cudaMalloc(&e->dyn_agent, sizeof(uint32_t) * n));
@@ -2375,17 +2437,23 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
   p.chunk_begin = tb;
   const int rows = steps + 1;  // + halo row for step tb-1
   CK(cudaMemsetAsync(e->ient_count, 0, sizeof(uint32_t), e->stream));
+  CK(cudaMemsetAsync(e->work_count, 0, sizeof(uint32_t) * 32, e->stream));
   CK(cudaMemsetAsync(e->scells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
   CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->dcells_stride * steps, e->stream));
   CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
   CK(cudaMemsetAsync(e->dyn_count, 0, sizeof(uint32_t), e->stream));
   const int gN = (e->N + 255) / 256;
   const int wide = 148 * 8;  // grid-stride kernels over the (device-side) dynamic count
+  const int groups = (rows + 7) >> 3;
+  {
+    Timed tm(e, CITAM_K_CLASSIFY);
+    k_classify<<<gN, 256, 0, e->stream>>>(p, tb, steps);
+    k_classify_dyn<<<wide / 2, 256, 0, e->stream>>>(p, tb, steps);
+    e->launches++;
+  }
   {
     Timed tm(e, CITAM_K_EXPAND_BIN);
-    k_classify<<<gN, 256, 0, e->stream>>>(p, tb, steps);
-    e->launches++;
-    k_expand_dyn<<<wide * 4, 128, 0, e->stream>>>(p, tb - 1, rows, 8);
+    k_expand_dyn<<<dim3(96, groups), 128, 0, e->stream>>>(p, tb - 1, rows);
   }
   launch_scan(e, e->scells, e->cells_stride, e->total_cells + 1, 1);
   launch_scan(e, e->cells, e->dcells_stride, e->dtotal_cells + 1, steps);
@@ -2393,7 +2461,7 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
   {
     Timed tm(e, CITAM_K_SCATTER);
     k_scatter_static<<<gN, 256, 0, e->stream>>>(p);
-    k_scatter_dyn<<<dim3(128, steps), 256, 0, e->stream>>>(p, steps);
+    k_scatter_dyn<<<dim3(48, steps), 256, 0, e->stream>>>(p, steps);
     k_select_changed_dyn<<<dim3(64, steps), 256, 0, e->stream>>>(p, steps, first ? 0 : -1);
     e->launches += 2;
   }
@@ -2632,7 +2700,7 @@ void citam_destroy(citam_engine* e) {
   for (auto p : e->adj_d) cudaFree(p);
   cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->window_d); cudaFree(e->pairs);
   cudaFree(e->coords); cudaFree(e->hist);
-  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->dur_out); cudaFree(e->ctr_d);
+  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->dur_out); cudaFree(e->sort_buf[0]); cudaFree(e->sort_buf[1]); cudaFree(e->ctr_d);
   cudaFree(e->flag_d); cudaFree(e->prev); cudaFree(e->states_d);
   cudaGetLastError();
   delete e;
@@ -3045,12 +3113,20 @@ int citam_export_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t 
   *n = have;
   if (have == 0) return CITAM_OK;
   if (capacity < have) return fail(CITAM_ERR_CAPACITY, "output holds %llu pairs, %llu needed", (unsigned long long)capacity, (unsigned long long)have);
-  PairEntry *a = nullptr, *b = nullptr;
-  if (cudaMalloc(&a, sizeof(PairEntry) * have) != cudaSuccess || cudaMalloc(&b, sizeof(PairEntry) * have) != cudaSuccess) {
-    cudaGetLastError();
-    cudaFree(a);
-    return fail(CITAM_ERR_CUDA, "out of device memory for the export of %llu pairs", (unsigned long long)have);
+  if (e->sort_bytes < sizeof(PairEntry) * have) {
+    cudaFree(e->sort_buf[0]); cudaFree(e->sort_buf[1]);
+    e->sort_buf[0] = e->sort_buf[1] = nullptr;
+    e->sort_bytes = 0;
+    const size_t want = sizeof(PairEntry) * (have + have / 8);
+    if (cudaMalloc(&e->sort_buf[0], want) != cudaSuccess || cudaMalloc(&e->sort_buf[1], want) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(e->sort_buf[0]);
+      e->sort_buf[0] = e->sort_buf[1] = nullptr;
+      return fail(CITAM_ERR_CUDA, "out of device memory for the export of %llu pairs", (unsigned long long)have);
+    }
+    e->sort_bytes = want;
   }
+  PairEntry *a = static_cast<PairEntry*>(e->sort_buf[0]), *b = static_cast<PairEntry*>(e->sort_buf[1]);
   CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
   {
     Timed tm(e, CITAM_K_FINALIZE);
@@ -3071,7 +3147,6 @@ int citam_export_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t 
     cudaError_t err = cudaStreamSynchronize(e->stream);
     if (err != cudaSuccess) rc = fail(CITAM_ERR_CUDA, "pair export failed: %s", cudaGetErrorString(err));
   }
-  cudaFree(a); cudaFree(b);
   return rc;
 }
 
@@ -3331,6 +3406,30 @@ int citam_statistics(citam_engine* e, citam_stats* out) {
   int rc = citam_statistics_begin(e);
   if (rc) return rc;
   return citam_statistics_end(e, out);
+}
+
+int citam_measure_random_updates(int32_t device, uint64_t table_bytes, uint64_t n_updates, int32_t probe_first, double* ms) {
+  if (!ms || table_bytes < 16 || n_updates == 0) return fail(CITAM_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(device));
+  unsigned long long words = 2;
+  while (words * 2 * 8 <= table_bytes) words *= 2;
+  unsigned long long* tab = nullptr;
+  CK(cudaMalloc(&tab, words * 8));
+  CK(cudaMemset(tab, 0, words * 8));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  k_random_updates<<<148 * 16, 256>>>(tab, words - 1, std::min<uint64_t>(n_updates, 1 << 20), probe_first);  // warm-up
+  CK(cudaEventRecord(a));
+  k_random_updates<<<148 * 16, 256>>>(tab, words - 1, n_updates, probe_first);
+  CK(cudaEventRecord(b));
+  CK(cudaEventSynchronize(b));
+  float t = 0;
+  CK(cudaEventElapsedTime(&t, a, b));
+  *ms = t;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(tab);
+  return CITAM_OK;
 }
 
 int citam_get_timings(citam_engine* e, citam_timings* out) {

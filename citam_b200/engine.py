@@ -287,6 +287,14 @@ class DeviceEngine:
         return {k: int(getattr(s, k)) for k, _ in L.Stats._fields_ if k != "reserved"}
 
 
+def measure_random_updates(table_bytes: int, n_updates: int, probe_first: bool = True, device: int = 0) -> float:
+    """Million random 8-byte read-modify-writes per second the device sustains over a table of `table_bytes`
+    (the ceiling for k_accumulate's access pattern); measurement aid, see the header."""
+    ms = C.c_double()
+    L.check(L.load().citam_measure_random_updates(device, table_bytes, n_updates, 1 if probe_first else 0, C.byref(ms)))
+    return n_updates / (ms.value * 1e-3) / 1e6
+
+
 def statistics_from_sums(s: Dict[str, int]):
     """The six statistics of ContactEvents.extract_statistics (contacts.py:185-294) from the
     device's integer sums, with Python's own division and round()."""

@@ -158,7 +158,7 @@ typedef struct {
                              however many chunks of the citam_run range it crosses        */
 } citam_counters;
 
-#define CITAM_N_KERNELS 8
+#define CITAM_N_KERNELS 9
 typedef struct {
   double ms[CITAM_N_KERNELS];      /* summed CUDA-event time per kernel kind */
   uint64_t launches[CITAM_N_KERNELS];
@@ -172,6 +172,7 @@ typedef struct {
 #define CITAM_K_FINALIZE 5
 #define CITAM_K_MISC 6
 #define CITAM_K_ACCUMULATE 7
+#define CITAM_K_CLASSIFY 8 /* per-chunk classification of the agents (split pipeline) */
 
 /* ---- life cycle -------------------------------------------------------- */
 int citam_abi_version(void);
@@ -231,6 +232,12 @@ int citam_clear_contact_log(citam_engine* e); /* drop exported records (block-wi
 int citam_statistics(citam_engine* e, citam_stats* out);
 int citam_get_counters(citam_engine* e, citam_counters* out);
 int citam_get_timings(citam_engine* e, citam_timings* out);
+/* Measurement aid (no engine): time n_updates 8-byte reductions at hashed addresses of a zeroed
+ * table of table_bytes (rounded down to a power of two) on `device`; probe_first != 0 adds the
+ * 16-byte slot load that precedes a pair-table update.  The rate is the memory system's ceiling for
+ * the accumulation kernel's access pattern (bench.py prints it beside the roofline line). */
+int citam_measure_random_updates(int32_t device, uint64_t table_bytes, uint64_t n_updates,
+                                 int32_t probe_first, double* ms);
 
 /* ---- multi-GPU: one scenario sharded by time ranges over G engines -------- */
 /* (the "timestep blocks" parallel runner the reference's docstring asks for,
