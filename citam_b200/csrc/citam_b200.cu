@@ -1683,19 +1683,6 @@ __device__ __forceinline__ citam_pair entry_to_pair(unsigned long long key, unsi
 }
 
 // the occupied slots of the pair table, packed (any order)
-__global__ void k_compact_entries(const PairEntry* tab, unsigned long long cap, PairEntry* out,
-                                  unsigned long long out_cap, DevCounters* ctr) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cap) return;
-  PairEntry e = tab[i];
-  if (e.key == 0ULL) return;
-  cg::coalesced_group g = cg::coalesced_threads();
-  unsigned long long base = 0;
-  if (g.thread_rank() == 0) base = atomicAdd(&ctr->export_cursor, (unsigned long long)g.size());
-  base = g.shfl(base, 0) + g.thread_rank();
-  if (base < out_cap) out[base] = e;
-}
-
 __global__ void k_entries_to_pairs(const PairEntry* in, unsigned long long n, citam_pair* out) {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1817,37 +1804,92 @@ __device__ __forceinline__ uint32_t part_of(unsigned long long key, uint32_t n_p
 }
 constexpr int kMaxParts = 64;
 
+// Both passes walk the table in tiles of 2048 slots per block; a warp owns 256 consecutive slots
+// (8 coalesced rounds of 32).  Lanes that share a destination are ranked with __match_any_sync and a
+// per-warp counter row in shared memory (no atomics); a block makes ONE global atomic per destination
+// and tile (it was one per warp and round on two addresses: 33 ms for a 2-way split of 1.25e8 pairs).
+constexpr int kPartRounds = 8;
+constexpr int kPartTile = 256 * kPartRounds;
+
 __global__ void __launch_bounds__(256) k_partition_count(const PairEntry* tab, unsigned long long cap, uint32_t n_parts,
                                                          unsigned long long* counts) {
-  __shared__ uint32_t c[kMaxParts];
-  if (threadIdx.x < kMaxParts) c[threadIdx.x] = 0;
+  __shared__ uint32_t wcount[8][kMaxParts];
+  for (int i = threadIdx.x; i < 8 * kMaxParts; i += 256) (&wcount[0][0])[i] = 0;
   __syncthreads();
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    unsigned long long key = tab[i].key;
-    if (key != 0ULL) atomicAdd(&c[part_of(key, n_parts)], 1u);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (unsigned long long tile = blockIdx.x; tile * kPartTile < cap; tile += gridDim.x) {
+    const unsigned long long wbase = tile * kPartTile + (unsigned long long)w * (32 * kPartRounds);
+#pragma unroll
+    for (int i = 0; i < kPartRounds; ++i) {
+      const unsigned long long idx = wbase + (unsigned long long)i * 32 + lane;
+      const unsigned long long key = idx < cap ? tab[idx].key : 0ULL;
+      const uint32_t part = key != 0ULL ? part_of(key, n_parts) : 0x100u + lane;  // empty slots match nobody
+      const unsigned peers = __match_any_sync(0xffffffffu, part);
+      if (key != 0ULL && lane == __ffs(peers) - 1) wcount[w][part] += __popc(peers);
+      __syncwarp();
+    }
   }
   __syncthreads();
-  if (threadIdx.x < n_parts && c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)c[threadIdx.x]);
+  if (threadIdx.x < n_parts) {
+    unsigned long long t = 0;
+    for (int ww = 0; ww < 8; ++ww) t += wcount[ww][threadIdx.x];
+    if (t) atomicAdd(&counts[threadIdx.x], t);
+  }
 }
 
-// cursors[part] starts at the part's first output index; one atomic per group of lanes with the same destination
+__device__ __forceinline__ void store_entry(citam_pair* out, unsigned long long o, const PairEntry& e) { out[o] = entry_to_pair(e.key, e.acc); }
+__device__ __forceinline__ void store_entry(PairEntry* out, unsigned long long o, const PairEntry& e) { out[o] = e; }
+
+// cursors[part] starts at the part's first output index.  Out = citam_pair: the send buffer of the
+// all-to-all; Out = PairEntry with n_parts == 1: the compaction in front of the ordered export.
+template <typename Out>
 __global__ void __launch_bounds__(256) k_partition_scatter(const PairEntry* tab, unsigned long long cap, uint32_t n_parts,
-                                                           unsigned long long* cursors, citam_pair* out,
+                                                           unsigned long long* cursors, Out* out,
                                                            unsigned long long out_cap) {
-  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < cap;
-       i0 += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long i = i0 + threadIdx.x;
-    PairEntry e; e.key = 0ULL; e.acc = 0ULL;
-    if (i < cap) e = tab[i];
-    const uint32_t part = e.key != 0ULL ? part_of(e.key, n_parts) : 0xffffffffu - (threadIdx.x & 31);
-    const unsigned peers = __match_any_sync(0xffffffffu, part);
-    if (e.key == 0ULL) continue;
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(&cursors[part], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1u));
-    if (base < out_cap) out[base] = entry_to_pair(e.key, e.acc);
+  __shared__ uint32_t wcount[8][kMaxParts];
+  __shared__ unsigned long long s_base[kMaxParts];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (unsigned long long tile = blockIdx.x; tile * kPartTile < cap; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < 8 * kMaxParts; i += 256) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned long long wbase = tile * kPartTile + (unsigned long long)w * (32 * kPartRounds);
+    PairEntry ent[kPartRounds];
+    uint32_t pos[kPartRounds];  // part | rank among the warp's earlier entries of that part << 8
+#pragma unroll
+    for (int i = 0; i < kPartRounds; ++i) {
+      const unsigned long long idx = wbase + (unsigned long long)i * 32 + lane;
+      ent[i].key = 0ULL; ent[i].acc = 0ULL;
+      if (idx < cap) ent[i] = tab[idx];
+      const bool valid = ent[i].key != 0ULL;
+      const uint32_t part = valid ? part_of(ent[i].key, n_parts) : 0x100u + lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, part);
+      const int leader = __ffs(peers) - 1;
+      uint32_t prev = 0;
+      if (valid && lane == leader) {
+        prev = wcount[w][part];
+        wcount[w][part] = prev + __popc(peers);
+      }
+      prev = __shfl_sync(0xffffffffu, prev, leader);
+      pos[i] = valid ? (part | ((prev + __popc(peers & lt)) << 8)) : 0xffffffffu;
+      __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < n_parts) {  // one reservation per destination and tile, then the warps in order
+      const int d = threadIdx.x;
+      uint32_t tot = 0;
+      for (int ww = 0; ww < 8; ++ww) { const uint32_t c = wcount[ww][d]; wcount[ww][d] = tot; tot += c; }
+      s_base[d] = tot ? atomicAdd(&cursors[d], (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPartRounds; ++i) {
+      if (pos[i] == 0xffffffffu) continue;
+      const uint32_t part = pos[i] & 0xffu;
+      const unsigned long long o = s_base[part] + wcount[w][part] + (pos[i] >> 8);
+      if (o < out_cap) store_entry(out, o, ent[i]);
+    }
+    __syncthreads();
   }
 }
 
@@ -2083,6 +2125,9 @@ struct citam_engine {
   unsigned long long* agent_dur = nullptr;
   uint32_t *agent_nev = nullptr, *agent_has = nullptr;
   unsigned long long* dur_out = nullptr;  // unpacked contact seconds (export scratch)
+  unsigned long long* part_cnt_d = nullptr;
+  uint32_t* sort_ws = nullptr;
+  size_t sort_ws_bytes = 0;
   void* sort_buf[2] = {nullptr, nullptr};  // ping-pong buffers of the ordered pair export, kept between calls
   size_t sort_bytes = 0;                   // (a first cudaMalloc of several GB costs hundreds of ms)
   bool counters_match = true;  // the per-agent counter words describe exactly the pairs in the table
@@ -2636,15 +2681,20 @@ static int device_sort(citam_engine* e, uint4* a, uint4* b, unsigned long long n
   *res = a;
   if (n < 2 || np == 0) return CITAM_OK;
   if (n >= (1ULL << 32)) return fail(CITAM_ERR_CAPACITY, "device sort holds fewer than 2^32 records");
-  uint32_t* ws = nullptr;
-  CK(cudaMalloc(&ws, rsort::workspace_bytes(n)));
+  const size_t ws_bytes = rsort::workspace_bytes(n);
+  if (e->sort_ws_bytes < ws_bytes) {  // kept between calls
+    cudaFree(e->sort_ws);
+    e->sort_ws = nullptr; e->sort_ws_bytes = 0;
+    CK(cudaMalloc(&e->sort_ws, ws_bytes + ws_bytes / 8));
+    e->sort_ws_bytes = ws_bytes + ws_bytes / 8;
+  }
+  uint32_t* ws = e->sort_ws;
   cudaError_t err;
   {
     Timed tm(e, CITAM_K_FINALIZE);
     err = rsort::sort(a, b, n, passes, np, ws, e->stream, key, res, &e->launches);
   }
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-  cudaFree(ws);
   if (err != cudaSuccess) return fail(CITAM_ERR_CUDA, "device sort failed: %s", cudaGetErrorString(err));
   return CITAM_OK;
 }
@@ -2700,7 +2750,7 @@ void citam_destroy(citam_engine* e) {
   for (auto p : e->adj_d) cudaFree(p);
   cudaFree(e->floors_d); cudaFree(e->segs_d); cudaFree(e->raw_d); cudaFree(e->seg_off_d); cudaFree(e->window_d); cudaFree(e->pairs);
   cudaFree(e->coords); cudaFree(e->hist);
-  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->dur_out); cudaFree(e->sort_buf[0]); cudaFree(e->sort_buf[1]); cudaFree(e->ctr_d);
+  cudaFree(e->log); cudaFree(e->agent_dur); cudaFree(e->agent_nev); cudaFree(e->agent_has); cudaFree(e->dur_out); cudaFree(e->sort_buf[0]); cudaFree(e->sort_buf[1]); cudaFree(e->part_cnt_d); cudaFree(e->sort_ws); cudaFree(e->ctr_d);
   cudaFree(e->flag_d); cudaFree(e->prev); cudaFree(e->states_d);
   cudaGetLastError();
   delete e;
@@ -3130,7 +3180,8 @@ int citam_export_pairs_device(citam_engine* e, citam_pair* out_device, uint64_t 
   CK(cudaMemsetAsync(&e->ctr_d->export_cursor, 0, sizeof(unsigned long long), e->stream));
   {
     Timed tm(e, CITAM_K_FINALIZE);
-    k_compact_entries<<<(unsigned)((e->pair_cap + 255) / 256), 256, 0, e->stream>>>(e->pairs, e->pair_cap, a, have, e->ctr_d);
+    const unsigned blocks = (unsigned)std::min<unsigned long long>(148 * 8, (e->pair_cap + kPartTile - 1) / kPartTile);
+    k_partition_scatter<PairEntry><<<blocks, 256, 0, e->stream>>>(e->pairs, e->pair_cap, 1u, &e->ctr_d->export_cursor, a, have);
   }
   CK(cudaGetLastError());
   rsort::Pass passes[12];
@@ -3469,10 +3520,12 @@ int citam_partition_pairs_device(citam_engine* e, citam_pair* out_device, uint64
   CK(cudaSetDevice(e->device));
   int rc = check_overflow(e);
   if (rc) return rc;
-  unsigned long long* cnt_d = nullptr;
-  CK(cudaMalloc(&cnt_d, sizeof(unsigned long long) * kMaxParts));
+  // per-destination counters / cursors: kept with the engine (a cudaMalloc + cudaFree pair per call cost more
+  // than both passes over the table)
+  if (!e->part_cnt_d) CK(cudaMalloc(&e->part_cnt_d, sizeof(unsigned long long) * kMaxParts));
+  unsigned long long* cnt_d = e->part_cnt_d;
   CK(cudaMemsetAsync(cnt_d, 0, sizeof(unsigned long long) * kMaxParts, e->stream));
-  const unsigned blocks = (unsigned)std::min<unsigned long long>(148 * 16, (e->pair_cap + 255) / 256);
+  const unsigned blocks = (unsigned)std::min<unsigned long long>(148 * 8, (e->pair_cap + kPartTile - 1) / kPartTile);
   {
     Timed tm(e, CITAM_K_FINALIZE);
     k_partition_count<<<blocks, 256, 0, e->stream>>>(e->pairs, e->pair_cap, (uint32_t)n_parts, cnt_d);
@@ -3484,17 +3537,15 @@ int citam_partition_pairs_device(citam_engine* e, citam_pair* out_device, uint64
   for (int k = 0; k < n_parts; ++k) { counts[k] = h[k]; cur[k] = tot; tot += h[k]; }
   for (int k = n_parts; k < kMaxParts; ++k) cur[k] = tot;
   if (tot > capacity) {
-    cudaFree(cnt_d);
     return fail(CITAM_ERR_CAPACITY, "output holds %llu pairs, %llu needed", (unsigned long long)capacity, tot);
   }
   if (tot) {
     CK(cudaMemcpyAsync(cnt_d, cur, sizeof cur, cudaMemcpyHostToDevice, e->stream));
     Timed tm(e, CITAM_K_FINALIZE);
-    k_partition_scatter<<<blocks, 256, 0, e->stream>>>(e->pairs, e->pair_cap, (uint32_t)n_parts, cnt_d, out_device, capacity);
+    k_partition_scatter<citam_pair><<<blocks, 256, 0, e->stream>>>(e->pairs, e->pair_cap, (uint32_t)n_parts, cnt_d, out_device, capacity);
   }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
-  cudaFree(cnt_d);
   return CITAM_OK;
 }
 
