@@ -687,6 +687,8 @@ def run_b200(args):
             "contacts_per_agent_step": contacts / max(1, units_rank),
             "pair_tests_per_s": pair_tests / ((phase["run_ms"] if args.mode == "day" else ms) * 1e-3),
             "table_updates_per_contact_step": runs / max(1, contacts),
+            "binned_fraction_of_agent_steps": (K if args.mode == "day" else 1) * c1.get("binned_agent_steps", 0) / max(1, units_rank)
+            if args.mode == "day" else (c1.get("binned_agent_steps", 0) - c0.get("binned_agent_steps", 0)) / max(1, units_rank),
             "day": day, "finalize": fin, "e2e_with_results": e2e_res, "mgpu_parity": parity,
         }
         print(json.dumps(line), file=_OUT, flush=True)

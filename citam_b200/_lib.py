@@ -52,7 +52,7 @@ class Counters(C.Structure):
         (n, C.c_uint64)
         for n in (
             "agent_steps", "pair_tests", "contact_steps", "kernel_launches",
-            "pair_slots_used", "coord_slots_used", "log_records", "overflow", "contact_runs",
+            "pair_slots_used", "coord_slots_used", "log_records", "overflow", "contact_runs", "binned_agent_steps",
         )
     ]
 

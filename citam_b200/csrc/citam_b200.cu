@@ -126,7 +126,7 @@ struct DevCounters {
   unsigned long long stats[6];
   unsigned long long contact_runs;
   unsigned long long merged_max_step;  // largest first-contact step of a merged record
-  unsigned long long pad[1];
+  unsigned long long binned;           // (agent, step) records binned per step
   unsigned long long cbuf_count[2][kSubBuffers * kCounterStride];  // one set per contact buffer
   unsigned long long pair_used_sub[kSubBuffers * kCounterStride];  // spread: inserts are frequent
 };
@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(256) k_select_changed_dyn(Params p, int rows /
   if (row >= rows) return;
   const int total = (int)p.cells[(size_t)row * p.dcells_stride + p.dtotal_cells];
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(&p.ctr->binned, (unsigned long long)total);
   for (int q0 = blockIdx.x * blockDim.x; q0 < total; q0 += gridDim.x * blockDim.x) {
     const int q = q0 + threadIdx.x;
     bool sel = false;
@@ -771,6 +772,7 @@ __global__ void __launch_bounds__(256) k_scatter(Params p, int rows /* S */, int
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   int row = blockIdx.y;
   if (a >= p.N || row >= rows) return;
+  if (a == 0) atomicAdd(&p.ctr->binned, (unsigned long long)p.cells[(size_t)row * p.cells_stride + p.total_cells]);
   if (p.window != nullptr) {  // 8 bytes instead of the 16-byte record for agents that are not around
     const int2 win = p.window[a];
     const int t = t_begin + row;
@@ -2086,6 +2088,15 @@ struct citam_engine {
   cudaStream_t stream2 = nullptr;  // k_accumulate of chunk i runs here while chunk i+1 is built on `stream`
   cudaEvent_t ev_built[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr};
   bool applied_pending[2] = {false, false};
+  // experiment (profiles/README.md; CITAM_DEFER_ACC=1): hold the accumulation of chunk i back until the
+  // pair kernel of chunk i + 1 is launched, so that the DRAM-bound kernel runs beside the
+  // instruction-bound one instead of beside the latency-bound binning kernels.  Measured: no gain
+  // (107.4 vs 107.3 ms per config-3 day) -- the step is bound by the sum of its kernels' work.
+  bool defer_acc = false;
+  bool acc_held = false;
+  int acc_held_cur = 0, acc_held_tb = 0;
+  Params acc_held_p{};
+  cudaEvent_t ev_go = nullptr;
   uint32_t* cells = nullptr;
   int4* sorted = nullptr;
   // split pipeline: static agents' records and classes are read by k_accumulate too -> double-buffered
@@ -2198,8 +2209,14 @@ struct Timed {
   }
 };
 
+static int release_accumulate(citam_engine* e);
+
 // Start building a chunk: take the other buffer set, once the accumulation that last read it is done.
 static int begin_chunk(citam_engine* e) {
+  if (e->acc_held && e->acc_held_cur == (e->cur ^ 1)) {  // the set about to be reused is still waiting to be applied
+    int rc = release_accumulate(e);
+    if (rc) return rc;
+  }
   e->cur ^= 1;
   e->rec = e->rec_buf[e->cur];
   e->cbuf = e->cbuf_buf[e->cur];
@@ -2212,6 +2229,8 @@ static int begin_chunk(citam_engine* e) {
 
 // Everything enqueued on the side stream happens before whatever follows on the engine's stream.
 static int join_side_stream(citam_engine* e) {
+  int rc0 = release_accumulate(e);
+  if (rc0) return rc0;
   for (int b = 0; b < 2; ++b)
     if (e->applied_pending[b]) {
       CK(cudaStreamWaitEvent(e->stream, e->ev_applied[b], 0));
@@ -2415,10 +2434,8 @@ static void launch_scan(citam_engine* e, uint32_t* cells, int stride, int n, int
 }
 
 // the chunk's contact buffer is applied on the side stream, overlapping the next chunk's build
-static int launch_accumulate(citam_engine* e, const Params& p, int t_begin) {
-  if (p.cbuf == nullptr) return CITAM_OK;
-  CK(cudaEventRecord(e->ev_built[e->cur], e->stream));
-  CK(cudaStreamWaitEvent(e->stream2, e->ev_built[e->cur], 0));
+static int issue_accumulate(citam_engine* e, const Params& p, int t_begin, int cur, cudaEvent_t after) {
+  CK(cudaStreamWaitEvent(e->stream2, after, 0));
   {
     Timed tm(e, CITAM_K_ACCUMULATE, e->stream2, true);
     const int nb = kSubBuffers * e->acc_blocks;
@@ -2428,9 +2445,30 @@ static int launch_accumulate(citam_engine* e, const Params& p, int t_begin) {
     k_reset_cbuf<<<1, kSubBuffers, 0, e->stream2>>>(p.cbuf_count);
     e->launches++;
   }
-  CK(cudaEventRecord(e->ev_applied[e->cur], e->stream2));
-  e->applied_pending[e->cur] = true;
+  CK(cudaEventRecord(e->ev_applied[cur], e->stream2));
+  e->applied_pending[cur] = true;
   return CITAM_OK;
+}
+
+// Launch the accumulation that is being held back (see citam_engine::defer_acc): it starts once
+// everything enqueued so far on the engine's stream is done.
+static int release_accumulate(citam_engine* e) {
+  if (!e->acc_held) return CITAM_OK;
+  e->acc_held = false;
+  CK(cudaEventRecord(e->ev_go, e->stream));
+  return issue_accumulate(e, e->acc_held_p, e->acc_held_tb, e->acc_held_cur, e->ev_go);
+}
+
+static int launch_accumulate(citam_engine* e, const Params& p, int t_begin) {
+  if (p.cbuf == nullptr) return CITAM_OK;
+  if (e->split && e->defer_acc) {
+    int rc = release_accumulate(e);  // at most one is held
+    if (rc) return rc;
+    e->acc_held = true; e->acc_held_cur = e->cur; e->acc_held_tb = t_begin; e->acc_held_p = p;
+    return CITAM_OK;
+  }
+  CK(cudaEventRecord(e->ev_built[e->cur], e->stream));
+  return issue_accumulate(e, p, t_begin, e->cur, e->ev_built[e->cur]);
 }
 
 // bin (already done by caller) -> scan -> scatter -> pairs for `rows` steps starting at t_begin
@@ -2509,6 +2547,10 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
     k_scatter_dyn<<<dim3(48, steps), 256, 0, e->stream>>>(p, steps);
     k_select_changed_dyn<<<dim3(64, steps), 256, 0, e->stream>>>(p, steps, first ? 0 : -1);
     e->launches += 2;
+  }
+  {
+    int rc = release_accumulate(e);  // the previous chunk's accumulation runs beside this chunk's pair kernel
+    if (rc) return rc;
   }
   {
     Timed tm(e, CITAM_K_PAIRS);
@@ -2642,6 +2684,8 @@ static int create_impl(citam_engine* e, const citam_config* cfg) {
   CK(cudaMalloc(&e->states_d, sizeof(citam_agent_state) * n));
   CK(cudaMallocHost(&e->snap_h, sizeof(DevCounters)));
   CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_go, cudaEventDisableTiming));
+  if (const char* g = getenv("CITAM_DEFER_ACC")) e->defer_acc = atoi(g) != 0;
   CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   for (int b = 0; b < 2; ++b) {
     CK(cudaEventCreateWithFlags(&e->ev_built[b], cudaEventDisableTiming));
@@ -2745,6 +2789,7 @@ void citam_destroy(citam_engine* e) {
   if (e->stream2) cudaStreamDestroy(e->stream2);
   for (int b = 0; b < 2; ++b) { if (e->ev_built[b]) cudaEventDestroy(e->ev_built[b]); if (e->ev_applied[b]) cudaEventDestroy(e->ev_applied[b]); }
   if (e->ev_snap) cudaEventDestroy(e->ev_snap);
+  if (e->ev_go) cudaEventDestroy(e->ev_go);
   if (e->snap_h) cudaFreeHost(e->snap_h);
   for (auto p : e->lut_d) cudaFree(p);
   for (auto p : e->adj_d) cudaFree(p);
@@ -3110,6 +3155,7 @@ int citam_get_counters(citam_engine* e, citam_counters* out) {
   out->log_records = std::min<unsigned long long>(c.log_count, e->log_cap);
   out->overflow = c.overflow;
   out->contact_runs = c.contact_runs;
+  out->binned_agent_steps = c.binned;
   return CITAM_OK;
 }
 

@@ -156,6 +156,9 @@ typedef struct {
   uint64_t overflow;      /* bit0 pair table, bit1 coord table, bit2 log          */
   uint64_t contact_runs;  /* table updates: a run of contact-steps of a stationary pair is one,
                              however many chunks of the citam_run range it crosses        */
+  uint64_t binned_agent_steps; /* (agent, step) records binned and sorted per step: every located
+                             agent-step with the contact log on; without it only the steps at which
+                             an agent is not covered by an entry of the per-chunk static array */
 } citam_counters;
 
 #define CITAM_N_KERNELS 9

@@ -57,7 +57,7 @@ def test_record_sizes_match_header():
     assert L.SEGMENT.itemsize == 20 and L.AGENT_STATE.itemsize == 12 and L.SPACE.itemsize == 32
     assert L.BOUNDARY.itemsize == 56 and L.DOOR.itemsize == 32 and L.PAIR.itemsize == 24
     assert L.COORD.itemsize == 24 and L.CONTACT.itemsize == 12
-    assert ctypes.sizeof(L.Config) == 56 and ctypes.sizeof(L.Counters) == 72 and ctypes.sizeof(L.Stats) == 48
+    assert ctypes.sizeof(L.Config) == 56 and ctypes.sizeof(L.Counters) == 80 and ctypes.sizeof(L.Stats) == 48
     assert "#define CITAM_ABI_VERSION %d" % L.ABI_VERSION in hdr
 
 
