@@ -187,20 +187,27 @@ struct Params {
   uint32_t* ient_rank;      // rank of the entry in its fine cell
   uint32_t* ient_count;
   uint8_t* dmask;           // [S][N] by dynamic index: 1 = the agent is binned at this step
-  uint32_t* need;           // [N] by dynamic index: bit g = rows 8g .. 8g+7 of the chunk hold a step at which the agent
+  unsigned long long* need; // [N] by dynamic index: bit g = rows 8g .. 8g+7 of the chunk hold a step at which the agent
                             // is binned, or the record before one (all other row groups are skipped by every kernel)
-  uint32_t* work;           // [32][N] per row group: the dynamic indices with that bit set
-  uint32_t* work_count;     // [32]
+  uint32_t* work;           // [kMaxGroups][N] per row group: the dynamic indices with that bit set
+  uint32_t* work_count;     // [kMaxGroups]
   int32_t chunk_steps;      // steps of the chunk being processed
   int32_t still_min;        // shortest stay that becomes an entry (>= kStillMin; larger than a chunk: none does)
   DevCounters* ctr;
 };
 constexpr uint32_t kClsOut = 0xFFFFFFFFu, kClsStatic = 0xFFFFFFFEu;
 constexpr int kStillMin = 16;       // shortest stay (steps inside the chunk) that becomes a static-array entry
-constexpr int kSplitMaxChunk = 240;  // `since` has 8 bits
-constexpr int kSplitDefaultChunk = 240;
+constexpr int kSplitMaxChunk = 495;  // `since` has 9 bits; 62 row groups of 8 rows hold the halo row + 495 steps
+constexpr int kMaxGroups = 64;
+constexpr int kSplitDefaultChunk = 480;
 // a static-array entry {xy, agent, state word | since << 16, until} is a candidate at row `row` (step t) iff
-__device__ __forceinline__ bool entry_valid(const int4& e, int row, int t) { return ((e.z >> 16) & 0xff) <= row + 1 && t < e.w; }
+// (`since` = first row of the stay, 9 bits: state-word bits 16-23 and bit 30, which static entries do not use otherwise)
+__device__ __forceinline__ int entry_since(int32_t z) { return ((z >> 16) & 0xff) | (((z >> 30) & 1) << 8); }
+__device__ __forceinline__ int32_t pack_since(int since) { return ((since & 0xff) << 16) | ((since >> 8) << 30); }
+__device__ __forceinline__ bool entry_valid(const int4& e, int row, int t) { return entry_since(e.z) <= row + 1 && t < e.w; }
+__device__ __forceinline__ unsigned long long bits_range(int a, int b) {  // bits a..b (0 <= a <= b <= 63)
+  return (b >= 63 ? ~0ULL : ((1ULL << (b + 1)) - 1ULL)) & ~((1ULL << a) - 1ULL);
+}
 // steps of [tb, tb + S) at which an agent standing in the zero-velocity segment [t0, next_t0) is unchanged
 __device__ __forceinline__ int still_len(int t0, int next_t0, int tb, int S) { return min(next_t0, tb + S) - max(t0 + 1, tb); }
 constexpr int kDynCellMul = 4;
@@ -335,10 +342,10 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
     if (t0 <= t) lo = mid + 1; else hi = mid;
   }
   long long c = lo - 1;
-  int4 s = make_int4(0, 0, 0, 0);
+  int4 s = make_int4(0, 0, 0, 0), nxs = make_int4(0, 0, 0, 0);  // the current segment and the one after it
   int next_t0 = INT_MAX;
   if (c >= sb) s = __ldg(&p.segs[c]);
-  if (c + 1 < se) next_t0 = __ldg(&p.segs[c + 1].x) & 0xffffff;
+  if (c + 1 < se) { nxs = __ldg(&p.segs[c + 1]); next_t0 = nxs.x & 0xffffff; }
   int lastx = INT_MIN, lasty = INT_MIN, lastf = -1, loc = -1;
   const int stride = coarse ? p.dcells_stride : p.cells_stride;
   // rows in groups of kGroup: the group's records are computed first, then its rank atomics are issued
@@ -358,10 +365,11 @@ __device__ __forceinline__ void expand_rows(const Params& p, int a, size_t slot,
       live[k] = row < row_end;
       if (!live[k]) continue;
       t = t_first + row;
-      while (t >= next_t0) {
+      while (t >= next_t0) {  // one 16-byte load per segment, a segment ahead of its use
         ++c;
-        s = __ldg(&p.segs[c]);
-        next_t0 = (c + 1 < se) ? (__ldg(&p.segs[c + 1].x) & 0xffffff) : INT_MAX;
+        s = nxs;
+        next_t0 = INT_MAX;
+        if (c + 1 < se) { nxs = __ldg(&p.segs[c + 1]); next_t0 = nxs.x & 0xffffff; }
       }
       out[k] = make_int4(0, 0, pack_fl(-1, -1), 0);
       if (t + 1 < win.x || t >= win.y) {  // outside the agent's window (see k_agent_windows)
@@ -502,32 +510,35 @@ __global__ void __launch_bounds__(256) k_classify(Params p, int tb, int S) {
 // or outside the agent's window is touched by no kernel.
 __global__ void __launch_bounds__(256) k_classify_dyn(Params p, int tb, int S) {
   const uint32_t Dn = *p.dyn_count;
-  const int groups = (S + 1 + 7) >> 3;
+  constexpr int gs = 3, G = 8;
+  const int groups = (S + 1 + G - 1) >> gs;
   const int lane = threadIdx.x & 31;
   for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < Dn; j0 += gridDim.x * blockDim.x) {  // whole warps iterate together
     const uint32_t j = j0 + threadIdx.x;
-    uint32_t need = 0;
+    unsigned long long need = 0;
     if (j < Dn) {
       const int a = (int)p.dyn_agent[j];
       const int2 win = p.window[a];
       const long long sb = p.seg_off[a], se = p.seg_off[a + 1];
-      need = groups >= 32 ? 0xffffffffu : (1u << groups) - 1u;
+      need = groups >= 64 ? ~0ULL : (1ULL << groups) - 1ULL;
       {
         // rows with step + 1 < win.x or step >= win.y carry nothing: rows [r_lo, r_hi) matter
         const long long r_lo = (long long)win.x - 1 - (tb - 1), r_hi = (win.y == INT_MAX) ? (1LL << 40) : (long long)win.y - (tb - 1);
-        for (int g = 0; g < groups; ++g)
-          if (8 * g + 7 < r_lo || 8 * g >= r_hi) need &= ~(1u << g);
+        // groups holding a row of [r_lo, r_hi): floor(r_lo / 8) .. floor((r_hi - 1) / 8)
+        const long long ga = r_lo <= 0 ? 0 : (r_lo >> gs), gb = r_hi > 8LL * 64 ? 63 : ((r_hi - 1) >> gs);
+        need &= (r_hi <= 0 || ga > 63 || gb < ga) ? 0ULL : bits_range((int)ga, (int)gb);
       }
       long long ci = sb + (long long)p.seg_cur[a] - 1;  // the segment holding step tb - 1 (k_classify found it)
-      int4 sg = make_int4(0, 0, 0, 0);
-      int next_t0 = INT_MAX;
+      // the walk keeps the next segment in registers: one 16-byte load per segment, issued a segment ahead
+      int4 sg = make_int4(0, 0, 0, 0), nx = make_int4(INT_MAX, 0, 0, 0);
       if (ci < sb) ci = sb;
       if (ci < se) {
         sg = __ldg(&p.segs[ci]);
-        next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
+        if (ci + 1 < se) nx = __ldg(&p.segs[ci + 1]);
       }
       while (ci < se) {
         const int t0 = sg.x & 0xffffff;
+        const int next_t0 = (ci + 1 < se) ? (nx.x & 0xffffff) : INT_MAX;
         if (t0 >= tb + S) break;
         if (sg.w == 0 && still_len(t0, next_t0, tb, S) >= p.still_min) {
           const int f = (sg.x >> 24) & 0xff;
@@ -536,34 +547,41 @@ __global__ void __launch_bounds__(256) k_classify_dyn(Params p, int tb, int S) {
             const FloorDev& fd = p.floors[f];
             const int32_t xy = (sg.y - fd.minx) | ((sg.z - fd.miny) << 16);
             const uint32_t rk = atomicAdd(&p.scells[cell_of_xy(p, fd, xy)], 1u);
-            const uint32_t e = atomicAdd(p.ient_count, 1u);
+            uint32_t e = 0;
+            {  // one reservation for the lanes that are here together
+              cg::coalesced_group cgp = cg::coalesced_threads();
+              if (cgp.thread_rank() == 0) e = atomicAdd(p.ient_count, (uint32_t)cgp.size());
+              e = cgp.shfl(e, 0) + cgp.thread_rank();
+            }
             const int since = max(t0 + 1, tb) - (tb - 1);
-            p.ient[e] = make_int4(xy, a, pack_fl(f, loc, 0, 0) | (since << 16), next_t0);
+            p.ient[e] = make_int4(xy, a, pack_fl(f, loc, 0, 0) | pack_since(since), next_t0);
             p.ient_rank[e] = rk;
             // covered rows [since, rb); the last one is kept when a step of the chunk follows it (it is
             // that step's previous record)
             const int rb = min(next_t0, tb + S) - (tb - 1);
             const int keep_from = (next_t0 < tb + S) ? rb - 1 : rb;
-            for (int g = (since + 7) >> 3; 8 * g + 7 < keep_from; ++g) need &= ~(1u << g);
+            // groups with every row in [since, keep_from): ceil(since / 8) .. floor((keep_from - 8) / 8)
+            const int ca = (since + G - 1) >> gs, cb = (keep_from - G) >> gs;
+            if (keep_from >= G && cb >= ca) need &= ~bits_range(ca, min(cb, 63));
           }
         }
         if (next_t0 >= tb + S) break;
         ++ci;
         if (ci >= se) break;
-        sg = __ldg(&p.segs[ci]);
-        next_t0 = (ci + 1 < se) ? (__ldg(&p.segs[ci + 1].x) & 0xffffff) : INT_MAX;
+        sg = nx;
+        if (ci + 1 < se) nx = __ldg(&p.segs[ci + 1]);
       }
       p.need[j] = need;
     }
     // per-group work lists: one reservation per warp and group, entries in lane (= dynamic index) order
     for (int g = 0; g < groups; ++g) {
-      const unsigned m = __ballot_sync(0xffffffffu, (need >> g) & 1u);
+      const unsigned m = __ballot_sync(0xffffffffu, (need >> g) & 1ULL);
       if (m == 0) continue;
       uint32_t base = 0;
       const int leader = __ffs(m) - 1;
       if (lane == leader) base = atomicAdd(&p.work_count[g], (uint32_t)__popc(m));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if ((need >> g) & 1u) p.work[(size_t)g * p.N + base + __popc(m & ((1u << lane) - 1u))] = j;
+      if ((need >> g) & 1ULL) p.work[(size_t)g * p.N + base + __popc(m & ((1u << lane) - 1u))] = j;
     }
   }
 }
@@ -2107,7 +2125,8 @@ struct citam_engine {
   int4* ient = nullptr;
   uint32_t *ient_rank = nullptr, *ient_count = nullptr;
   uint8_t* dmask = nullptr;
-  uint32_t *need = nullptr, *work = nullptr, *work_count = nullptr;
+  unsigned long long* need = nullptr;
+  uint32_t *work = nullptr, *work_count = nullptr;
   int chunk_steps = 0;
   int still_min = kStillMin;  // CITAM_STILL_MIN (>= kStillMin; e.g. 100000 keeps every dynamic agent in the per-step arrays)
   int dtotal_cells = 0, dcells_stride = 4;
@@ -2302,7 +2321,7 @@ static void free_chunk(citam_engine* e) {
   cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count); cudaFree(e->seg_cur);
   cudaFree(e->ient); cudaFree(e->ient_rank); cudaFree(e->ient_count); cudaFree(e->dmask); cudaFree(e->need); cudaFree(e->work); cudaFree(e->work_count);
   e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = e->seg_cur = nullptr;
-  e->ient = nullptr; e->ient_rank = e->ient_count = e->need = e->work = e->work_count = nullptr; e->dmask = nullptr;
+  e->ient = nullptr; e->ient_rank = e->ient_count = e->work = e->work_count = nullptr; e->need = nullptr; e->dmask = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -2390,9 +2409,9 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->ient, sizeof(int4) * n_stays));
   CK(cudaMalloc(&e->ient_rank, sizeof(uint32_t) * n_stays));
   CK(cudaMalloc(&e->ient_count, sizeof(uint32_t)));
-  CK(cudaMalloc(&e->need, sizeof(uint32_t) * n));
-  CK(cudaMalloc(&e->work, (e->log_cap == 0 && !e->no_split) ? sizeof(uint32_t) * n * 32 : 4));
-  CK(cudaMalloc(&e->work_count, sizeof(uint32_t) * 32));
+  CK(cudaMalloc(&e->need, sizeof(unsigned long long) * n));
+  CK(cudaMalloc(&e->work, (e->log_cap == 0 && !e->no_split) ? sizeof(uint32_t) * n * (size_t)std::min(kMaxGroups, (std::min(S, kSplitMaxChunk) + 8) / 8) : 4));
+  CK(cudaMalloc(&e->work_count, sizeof(uint32_t) * kMaxGroups));
   CK(cudaMalloc(&e->dmask, (e->log_cap == 0 && !e->no_split) ? n * (size_t)S : 1));
   CK(cudaMalloc(&e->scells, sizeof(uint32_t) * (size_t)e->cells_stride));
   CK(cudaMalloc(&e->dyn_agent, sizeof(uint32_t) * n));
@@ -2408,7 +2427,7 @@ static int pick_chunk(citam_engine* e, int steps) {
   if (e->cfg.steps_per_chunk > 0) return std::min(std::min(steps, e->cfg.steps_per_chunk), split_mode ? kSplitMaxChunk : kMaxChunk);
   // ~64M agent-steps per launch group (3.3 GiB of per-step records), bounded by 1 GiB of histogram rows
   const bool split = e->log_cap == 0 && !e->no_split;
-  long long by_agents = std::max(1LL, ((split ? 256LL : 64LL) << 20) / std::max(1, e->N));
+  long long by_agents = std::max(1LL, ((split ? 512LL : 64LL) << 20) / std::max(1, e->N));
   long long by_cells = std::max(1LL, (1LL << 28) / std::max(4, e->cells_stride));
   long long s = std::min(by_agents, by_cells);
   // without the contact log (split pipeline) an agent is binned once per chunk if it stands still for
@@ -2520,7 +2539,7 @@ static int run_split_chunk(citam_engine* e, int tb, int steps) {
   p.chunk_begin = tb;
   const int rows = steps + 1;  // + halo row for step tb-1
   CK(cudaMemsetAsync(e->ient_count, 0, sizeof(uint32_t), e->stream));
-  CK(cudaMemsetAsync(e->work_count, 0, sizeof(uint32_t) * 32, e->stream));
+  CK(cudaMemsetAsync(e->work_count, 0, sizeof(uint32_t) * kMaxGroups, e->stream));
   CK(cudaMemsetAsync(e->scells, 0, sizeof(uint32_t) * (size_t)e->cells_stride, e->stream));
   CK(cudaMemsetAsync(e->cells, 0, sizeof(uint32_t) * (size_t)e->dcells_stride * steps, e->stream));
   CK(cudaMemsetAsync(e->chg_count, 0, sizeof(uint32_t) * 32 * steps, e->stream));
