@@ -548,7 +548,7 @@ def run_b200(args):
         roof = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic,
-            "traffic_source": "profiles/%s (one launch of the same build, a 128-step chunk of 1e6 agents)" % PROFILE_CSV,
+            "traffic_source": "profiles/%s (one launch of the same build, a 480-step chunk of 1e6 agents)" % PROFILE_CSV,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": avg_ms,
             "algorithmic_bytes_rule": "k_accumulate: 64 B x table updates applied (one per contact run); position kernels: "

@@ -7,24 +7,36 @@
 //   CloseContactsCalculator.run               citam/engine/calculators/close_contacts_calculator.py:64-231
 //   ContactEvents.add_contact / statistics    citam/engine/calculators/contacts.py:92-294
 //
-// Pipeline per chunk of S <= 1024 time steps (one launch per stage covers all steps of the chunk;
-// every accumulator is commutative, so steps, chunks and time blocks are independent):
-//   k_expand_bin      itinerary segments -> per-step 16-byte records {xy, until, state word, rank};
-//                     one atomic per located agent returns its rank in its uniform-grid cell
-//   k_scan(+_add)     per-step exclusive scan of the cell histogram (rows x pieces CTAs)
-//   k_scatter         counting-sort scatter into cell order (16-byte records)
-//   k_select_changed  per step, the agents whose state may differ from the step before, in cell order
-//   k_pairs           first step of a citam_run RANGE only: every located agent against its half
-//                     neighbourhood (own cell tail, right cell, 3 cells above), window in shared memory
-//   k_pairs_changed   every other step: only changed agents, 3x3 neighbourhood, tests flattened over
-//                     a 256-agent batch; a contact of two unchanged agents is inside a run that an
-//                     earlier step added in one piece (stationary-run aggregation: ONE table update
-//                     per contact run, however many chunks the run crosses)
-//   k_accumulate      (side stream, overlaps the next chunk) one contact-run record per thread:
-//                     16-byte pair-table slot probe + one reduction, one 64-bit reduction into the dense
-//                     per-coordinate histogram, two reductions into the L2-resident per-agent counters
+// Two step pipelines; every accumulator is commutative, so steps, chunks and time ranges are independent.
+//
+// citam_run without the contact log -- the SPLIT pipeline, per chunk of S <= 495 steps (one launch per
+// stage covers all steps of the chunk):
+//   k_classify        per agent: out / static (stands in one zero-velocity segment from the halo step to
+//                     the chunk's end: binned ONCE, fine grid) / dynamic (dense index)
+//   k_classify_dyn    per dynamic agent: its stays of >= 16 steps inside the chunk become entries of the
+//                     same static array, valid for [since, until); the 8-row groups that still hold a
+//                     binned step go into per-group work lists
+//   k_scan(+_add)     exclusive scans of the static cell histogram and of the per-step dynamic ones
+//   k_scatter_static  counting-sort scatter of the static array
+//   k_expand_dyn      work-list entries -> per-step 16-byte records {xy, until, state word, rank} of the
+//                     steps no stay covers; one atomic per binned record returns its rank in its coarse cell
+//   k_scatter_dyn, k_select_changed_dyn   per-step counting-sort scatter; the changed agents of each step
+//   k_pairs           first step of a citam_run RANGE only: static-static pairs, half neighbourhood,
+//                     candidate window in shared memory
+//   k_pairs_changed_split   every step: only changed agents, against 3x3 fine cells of the static array and
+//                     3x3 coarse cells of the step's dynamic array, tests flattened over a 128-agent batch;
+//                     a contact of two unchanged agents is inside a run that an earlier step added in one
+//                     piece (stationary-run aggregation: ONE table update per contact run, however many
+//                     chunks the run crosses)
+//   k_accumulate      (side stream) contact-run records -> 16-byte pair-table slot probe + one reduction,
+//                     one 64-bit reduction into the dense per-coordinate histogram, two reductions into
+//                     the L2-resident per-agent words (contact seconds | contact events << 40)
+// With the contact log (full-fidelity writers), for citam_step_states and under CITAM_NO_SPLIT=1 every
+// agent is expanded and binned at every step: k_expand_bin, k_scan, k_scatter, k_select_changed,
+// k_pairs / k_pairs_changed, k_accumulate.
 // Finalize (K5): compaction of the tables + device radix sort (radix_sort.cuh) into the reference's
-// output order; partition by key hash for the multi-GPU all-to-all; merge of received records.
+// output order; partition by key hash for the multi-GPU all-to-all; merge of received records;
+// statistics from the per-agent words (O(n_agents), no pass over the pair table).
 // The distance predicate is the reference's float64 sqrt(dx^2+dy^2) < D as an exact integer
 // threshold (find_s_max).  All of this is HBM/L2-bound integer work; there is no GEMM in the path.
 

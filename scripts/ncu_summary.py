@@ -20,6 +20,14 @@ METRICS = [
 UNIT = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3, "s": 1e3}
 
 
+def clean(name):
+    """kernel name without return type, template arguments and parameter list"""
+    n = name.split("(")[0]
+    if n.startswith("void "):
+        n = n[5:]
+    return n.split("<")[0]
+
+
 def launches(path, prefix):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -33,7 +41,7 @@ def launches(path, prefix):
             if len(r) <= vi:
                 continue
             ms = float(r[vi].replace(",", "")) * UNIT.get(r[ui], 1.0)
-            name = r[ki].split("(")[0]
+            name = clean(r[ki])
             tot[name] += ms
             cnt[name] += 1
             w.writerow([r[0], name, r[gi], r[bi], "%.3f" % (ms * 1e3)])
@@ -53,7 +61,7 @@ def full(rep, out):
     kn = hdr.index("Kernel Name")
     names = []
     for r in rows[2:]:
-        n = r[kn].split("(")[0]
+        n = clean(r[kn])
         names.append(n + ("#%d" % (sum(1 for x in names if x.split("#")[0] == n) + 1) if any(x.split("#")[0] == n for x in names) else ""))
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
