@@ -1841,6 +1841,7 @@ constexpr int kMaxParts = 64;
 // per-warp counter row in shared memory (no atomics); a block makes ONE global atomic per destination
 // and tile (it was one per warp and round on two addresses: 33 ms for a 2-way split of 1.25e8 pairs).
 constexpr int kPartRounds = 8;
+constexpr uint32_t kBallotParts = 8;
 constexpr int kPartTile = 256 * kPartRounds;
 
 __global__ void __launch_bounds__(256) k_partition_count(const PairEntry* tab, unsigned long long cap, uint32_t n_parts,
@@ -1856,8 +1857,15 @@ __global__ void __launch_bounds__(256) k_partition_count(const PairEntry* tab, u
       const unsigned long long idx = wbase + (unsigned long long)i * 32 + lane;
       const unsigned long long key = idx < cap ? tab[idx].key : 0ULL;
       const uint32_t part = key != 0ULL ? part_of(key, n_parts) : 0x100u + lane;  // empty slots match nobody
-      const unsigned peers = __match_any_sync(0xffffffffu, part);
-      if (key != 0ULL && lane == __ffs(peers) - 1) wcount[w][part] += __popc(peers);
+      if (n_parts <= kBallotParts) {  // a ballot per destination is cheaper than match.any for a few destinations
+        for (uint32_t d = 0; d < n_parts; ++d) {
+          const unsigned m = __ballot_sync(0xffffffffu, part == d);
+          if (lane == 0 && m) wcount[w][d] += __popc(m);
+        }
+      } else {
+        const unsigned peers = __match_any_sync(0xffffffffu, part);
+        if (key != 0ULL && lane == __ffs(peers) - 1) wcount[w][part] += __popc(peers);
+      }
       __syncwarp();
     }
   }
@@ -1895,8 +1903,16 @@ __global__ void __launch_bounds__(256) k_partition_scatter(const PairEntry* tab,
       if (idx < cap) ent[i] = tab[idx];
       const bool valid = ent[i].key != 0ULL;
       const uint32_t part = valid ? part_of(ent[i].key, n_parts) : 0x100u + lane;
-      const unsigned peers = __match_any_sync(0xffffffffu, part);
-      const int leader = __ffs(peers) - 1;
+      unsigned peers = 0;
+      if (n_parts <= kBallotParts) {
+        for (uint32_t d = 0; d < n_parts; ++d) {
+          const unsigned m = __ballot_sync(0xffffffffu, part == d);
+          if (part == d) peers = m;
+        }
+      } else {
+        peers = __match_any_sync(0xffffffffu, part);
+      }
+      const int leader = valid ? __ffs(peers) - 1 : lane;
       uint32_t prev = 0;
       if (valid && lane == leader) {
         prev = wcount[w][part];

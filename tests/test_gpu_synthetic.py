@@ -46,7 +46,7 @@ def test_device_lut_equals_rectangle_rule(synth):
     eng.close()
 
 
-@pytest.mark.parametrize("chunk,no_split", [(0, 0), (37, 0), (5, 0), (37, 1)])
+@pytest.mark.parametrize("chunk,no_split", [(0, 0), (37, 0), (5, 0), (249, 0), (495, 0), (37, 1)])
 def test_tables_bit_exact_vs_grid_oracle(synth, chunk, no_split, monkeypatch):
     """Both step pipelines: the static/dynamic split (default without a contact log) and the one that
     expands and bins every agent at every step (CITAM_NO_SPLIT=1)."""
