@@ -337,10 +337,12 @@ def default_pair_cap(args, p, world):
         return int(min(1 << 31, max(1 << 22, 2048 * N)))
     # whole day: ~250 distinct pairs per agent and day on these crowded floors (measured, config 3: 2.5e8 pairs);
     # a rank's table holds its own range's pairs before the exchange and its share of all pairs after it
-    # (pairs that meet in several ranks' ranges are held by each of them: twice the even share is allowed
-    # for).  The table is at most half full at these sizes; a table that overflows aborts the bench.
+    # (pairs that meet in several ranks' ranges are held by each of them; measured: the ranks' tables together
+    # hold ~1.0 x the day's pairs at 2-8 ranks; 1.3 x the even share is allowed for).  The table is at most
+    # a third full at these sizes (every pass over it -- reset, partition, clear -- costs its capacity);
+    # a table that overflows aborts the bench.
     est = {"config5": 4096}.get(args.workload, 320) * N
-    per_rank = est if world == 1 else 2 * est // world
+    per_rank = est if world == 1 else int(1.3 * est / world)
     cap = 1 << 22
     while cap < 2 * per_rank:
         cap <<= 1

@@ -220,9 +220,17 @@ class ShardedRun:
                     eng.merge(np.zeros(0, PAIR), gc[r])
         ev[1].record()
         # pair table: partition -> all-to-all -> merge
+        import time
+
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
         n_local = eng.pair_count()
+        w1 = time.perf_counter()
         send = torch.empty((max(1, n_local), 3), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        w2 = time.perf_counter()
         counts = eng.partition_pairs_device(send.data_ptr(), n_local, G)
+        w3 = time.perf_counter()
         ev[2].record()
         send_counts = torch.from_numpy(counts.astype(np.int64)).cuda()
         recv_counts = torch.empty_like(send_counts)
@@ -248,6 +256,7 @@ class ShardedRun:
             "allreduce_ms": ev[0].elapsed_time(ev[1]), "partition_ms": ev[1].elapsed_time(ev[2]),
             "all_to_all_ms": ev[2].elapsed_time(ev[3]), "clear_and_merge_ms": ev[3].elapsed_time(ev[4]),
             "statistics_ms": ev[4].elapsed_time(ev[5]),
+            "partition_host_ms": {"pair_count": 1e3 * (w1 - w0), "send_buffer": 1e3 * (w2 - w1), "partition_call": 1e3 * (w3 - w2)},
         }
         return sums
 
