@@ -199,9 +199,9 @@ struct Params {
   uint32_t* ient_rank;      // rank of the entry in its fine cell
   uint32_t* ient_count;
   uint8_t* dmask;           // [S][N] by dynamic index: 1 = the agent is binned at this step
-  unsigned long long* need; // [N] by dynamic index: bit g = rows 8g .. 8g+7 of the chunk hold a step at which the agent
-                            // is binned, or the record before one (all other row groups are skipped by every kernel)
-  uint32_t* work;           // [kMaxGroups][N] per row group: the dynamic indices with that bit set
+  uint32_t* work;           // [kMaxGroups][N] per group of 8 rows: the dynamic agents (by dynamic index) with a step in it
+                            // at which they are binned, or the record before one (k_classify_dyn); every other
+                            // row group of an agent is skipped by every kernel
   uint32_t* work_count;     // [kMaxGroups]
   int32_t chunk_steps;      // steps of the chunk being processed
   int32_t still_min;        // shortest stay that becomes an entry (>= kStillMin; larger than a chunk: none does)
@@ -583,7 +583,6 @@ __global__ void __launch_bounds__(256) k_classify_dyn(Params p, int tb, int S) {
         sg = nx;
         if (ci + 1 < se) nx = __ldg(&p.segs[ci + 1]);
       }
-      p.need[j] = need;
     }
     // per-group work lists: one reservation per warp and group, entries in lane (= dynamic index) order
     for (int g = 0; g < groups; ++g) {
@@ -2153,7 +2152,6 @@ struct citam_engine {
   int4* ient = nullptr;
   uint32_t *ient_rank = nullptr, *ient_count = nullptr;
   uint8_t* dmask = nullptr;
-  unsigned long long* need = nullptr;
   uint32_t *work = nullptr, *work_count = nullptr;
   int chunk_steps = 0;
   int still_min = kStillMin;  // CITAM_STILL_MIN (>= kStillMin; e.g. 100000 keeps every dynamic agent in the per-step arrays)
@@ -2330,7 +2328,7 @@ static Params make_params(citam_engine* e) {
   if (e->split) {
     p.cls = e->cls_buf[e->cur]; p.srec = e->srec_buf[e->cur];
     p.ssorted = e->ssorted; p.scells = e->scells; p.dyn_agent = e->dyn_agent; p.dyn_count = e->dyn_count; p.seg_cur = e->seg_cur;
-    p.ient = e->ient; p.ient_rank = e->ient_rank; p.ient_count = e->ient_count; p.dmask = e->dmask; p.need = e->need; p.work = e->work; p.work_count = e->work_count;
+    p.ient = e->ient; p.ient_rank = e->ient_rank; p.ient_count = e->ient_count; p.dmask = e->dmask; p.work = e->work; p.work_count = e->work_count;
     p.chunk_steps = e->chunk_steps; p.still_min = e->still_min;
   }
   p.ctr = e->ctr_d;
@@ -2347,9 +2345,9 @@ static void free_chunk(citam_engine* e) {
   e->chg_list = e->chg_count = e->part_sums = nullptr;
   for (int b = 0; b < 2; ++b) { cudaFree(e->srec_buf[b]); cudaFree(e->cls_buf[b]); e->srec_buf[b] = nullptr; e->cls_buf[b] = nullptr; }
   cudaFree(e->ssorted); cudaFree(e->scells); cudaFree(e->dyn_agent); cudaFree(e->dyn_count); cudaFree(e->seg_cur);
-  cudaFree(e->ient); cudaFree(e->ient_rank); cudaFree(e->ient_count); cudaFree(e->dmask); cudaFree(e->need); cudaFree(e->work); cudaFree(e->work_count);
+  cudaFree(e->ient); cudaFree(e->ient_rank); cudaFree(e->ient_count); cudaFree(e->dmask); cudaFree(e->work); cudaFree(e->work_count);
   e->ssorted = nullptr; e->scells = e->dyn_agent = e->dyn_count = e->seg_cur = nullptr;
-  e->ient = nullptr; e->ient_rank = e->ient_count = e->work = e->work_count = nullptr; e->need = nullptr; e->dmask = nullptr;
+  e->ient = nullptr; e->ient_rank = e->ient_count = e->work = e->work_count = nullptr; e->dmask = nullptr;
   e->rec = nullptr; e->cells = nullptr; e->sorted = nullptr;
   e->cbuf = nullptr; e->cbuf_cap = 0;
   e->S = 0;
@@ -2437,7 +2435,6 @@ static int ensure_ready(citam_engine* e, int want_steps) {
   CK(cudaMalloc(&e->ient, sizeof(int4) * n_stays));
   CK(cudaMalloc(&e->ient_rank, sizeof(uint32_t) * n_stays));
   CK(cudaMalloc(&e->ient_count, sizeof(uint32_t)));
-  CK(cudaMalloc(&e->need, sizeof(unsigned long long) * n));
   CK(cudaMalloc(&e->work, (e->log_cap == 0 && !e->no_split) ? sizeof(uint32_t) * n * (size_t)std::min(kMaxGroups, (std::min(S, kSplitMaxChunk) + 8) / 8) : 4));
   CK(cudaMalloc(&e->work_count, sizeof(uint32_t) * kMaxGroups));
   CK(cudaMalloc(&e->dmask, (e->log_cap == 0 && !e->no_split) ? n * (size_t)S : 1));
