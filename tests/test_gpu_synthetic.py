@@ -115,6 +115,31 @@ def test_time_blocks_in_any_order_and_merge(synth):
     b.close()
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_time_ranges_in_random_order(synth, seed):
+    """Ranges of random length (1 step to several chunks, nothing aligned) run in shuffled order on two
+    engines and merged: the first step of every range owns what it finds, stays and contact runs are
+    clipped at every range end, the cursors jump back and forth -- the tables still equal a straight run."""
+    fac, seg_off, segs, p, T, want, _ = synth
+    rng = np.random.default_rng(seed)
+    cuts = [0]
+    while cuts[-1] < T:
+        cuts.append(min(T, cuts[-1] + int(rng.choice([1, 2, 7, 15, 16, 17, 40, 130, 260, 700]))))
+    ranges = list(zip(cuts[:-1], cuts[1:]))
+    order = rng.permutation(len(ranges))
+    a = _engine(fac, seg_off, segs, p, steps_per_chunk=int(rng.choice([0, 23, 250])))
+    b = _engine(fac, seg_off, segs, p)
+    for k in order:
+        (a if rng.random() < 0.5 else b).run(*ranges[k])
+    dur_b = b.agent_durations()
+    a.merge(b.pairs(), b.coords())
+    got = tables_of(a)
+    assert got[0] == want[0] and got[1] == want[1]
+    assert [int(x) + int(y) for x, y in zip(got[2], dur_b)] == want[2]
+    a.close()
+    b.close()
+
+
 def test_auto_capacity_grows(synth):
     """Library-chosen pair capacity starts small and is doubled while more than a quarter full."""
     fac, seg_off, segs, p, T, want, _ = synth
