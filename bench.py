@@ -597,9 +597,14 @@ def run_b200(args):
         sg_p = torch.from_numpy(np.ascontiguousarray(segs).view(np.uint8)).pin_memory()
         out_dur = torch.empty(N, dtype=torch.int64).pin_memory()
         h2d_step = so_p.numel() * 8 + sg_p.numel()
+        h2d_rank = [h2d_step]
 
         def e2e_step(s):
-            eng.load_segments_raw(so_p.data_ptr(), sg_p.data_ptr(), len(segs))
+            if sharded is not None:
+                # every rank holds the store in pinned host memory; each uploads 1/G of it, NVLink all-gathers it
+                h2d_rank[0] = sharded.load_store(so_p, sg_p, len(segs))
+            else:
+                eng.load_segments_raw(so_p.data_ptr(), sg_p.data_ptr(), len(segs))
             step(s)
             eng.agent_durations_into(out_dur.data_ptr())
 
@@ -616,8 +621,11 @@ def run_b200(args):
         ms_e = max_over_ranks(ev[0].elapsed_time(ev[1]))
         e2e = {
             "value": units_all / (ms_e * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": N * 8,
-            "api": "citam_load_itineraries(whole store, pinned host) + " + (
+            "h2d_bytes_per_step": int(h2d_step if sharded is None else h2d_rank[0] * world), "d2h_bytes_per_step": N * 8 * world,
+            "h2d_bytes_per_step_and_rank": int(h2d_rank[0]),
+            "api": ("citam_load_itineraries(whole store, pinned host) + " if sharded is None else
+                    "ShardedRun.load_store (1/G of the store from pinned host memory per rank + NCCL all-gather + "
+                    "citam_load_itineraries from the device buffer) + ") + (
                 "citam_reset + citam_run(this rank's range) + final exchange + citam_statistics" if args.mode == "day"
                 else "citam_run(block)") + " + citam_export_agent_durations",
         }

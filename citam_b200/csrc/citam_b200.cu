@@ -2989,7 +2989,9 @@ int citam_load_itineraries(citam_engine* e, const int64_t* seg_off, const citam_
   citam_segment* raw = e->raw_d;
   CK(cudaMemsetAsync(e->flag_d, 0, sizeof(int), e->stream));
   CK(cudaMemcpyAsync(e->seg_off_d, seg_off, sizeof(long long) * ((size_t)e->N + 1), cudaMemcpyHostToDevice, e->stream));
-  if (n_segs) CK(cudaMemcpyAsync(raw, segs, sizeof(citam_segment) * n_segs, cudaMemcpyHostToDevice, e->stream));
+  // `segs` may be a host or a DEVICE pointer (unified addressing): a multi-GPU run uploads 1/G of the store per
+  // rank and all-gathers it over NVLink (distributed.ShardedRun.load_store)
+  if (n_segs) CK(cudaMemcpyAsync(raw, segs, sizeof(citam_segment) * n_segs, cudaMemcpyDefault, e->stream));
   {
     // the documented limits, checked on the device copy (no host pass over 10^7-10^8 records)
     Timed tm(e, CITAM_K_MISC);

@@ -183,6 +183,30 @@ class ShardedRun:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.info: Dict[str, float] = {}
 
+    def load_store(self, seg_off_host, segs_host_bytes, n_segs: int):
+        """Load ONE itinerary store, held in (pinned) host memory on every rank, into all ranks' engines
+        with 1/G of the host-to-device traffic per rank: rank r uploads the r-th of G equal byte ranges of
+        the segment array, an NCCL all-gather over NVLink completes it on every GPU, and the engine loads it
+        from the device buffer.  `seg_off_host`: torch int64 [n_agents + 1]; `segs_host_bytes`: torch uint8
+        view of the citam_segment records.  Returns the bytes this rank copied from the host."""
+        import torch
+
+        dist = _dist()
+        G, r = self.world, self.rank
+        total = int(segs_host_bytes.numel())
+        chunk = (total + G - 1) // G
+        chunk = (chunk + 255) // 256 * 256
+        if getattr(self, "_store", None) is None or self._store.numel() != G * chunk:
+            self._store = torch.empty(G * chunk, dtype=torch.uint8, device="cuda")
+            self._part = torch.empty(chunk, dtype=torch.uint8, device="cuda")
+        lo, hi = min(total, r * chunk), min(total, (r + 1) * chunk)
+        if hi > lo:
+            self._part[: hi - lo].copy_(segs_host_bytes[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(self._store, self._part)
+        torch.cuda.current_stream().synchronize()
+        self.engine.load_segments_raw(seg_off_host.data_ptr(), self._store.data_ptr(), n_segs)
+        return (hi - lo) + int(seg_off_host.numel()) * 8
+
     def plan(self) -> List[Tuple[int, int]]:
         if self.block is None:
             return [plan_range(self.T, self.world, self.rank)]

@@ -201,6 +201,7 @@ int citam_get_floor_lut(citam_engine* e, int32_t floor, int16_t* out /* [H*W] */
 int citam_set_floor_adjacency(citam_engine* e, int32_t floor, int32_t n_spaces, const uint8_t* adj);
 
 /* ---- itineraries: replaces Schedule.itinerary / get_next_position ------- */
+/* seg_off is a host array; segs may be a host or a device pointer (unified addressing). */
 int citam_load_itineraries(citam_engine* e, const int64_t* seg_off /* [n_agents+1] */,
                            const citam_segment* segs, int64_t n_segs);
 

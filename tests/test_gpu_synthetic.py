@@ -140,6 +140,21 @@ def test_random_time_ranges_in_random_order(synth, seed):
     b.close()
 
 
+def test_itinerary_store_from_a_device_buffer(synth):
+    """citam_load_itineraries takes the segment records from a device pointer too (the multi-GPU store
+    distribution all-gathers them over NVLink): same tables as from the host arrays."""
+    import torch
+
+    fac, seg_off, segs, p, T, want, _ = synth
+    eng = _engine(fac, seg_off, segs, p)
+    so = np.ascontiguousarray(seg_off, np.int64)
+    dev = torch.from_numpy(np.ascontiguousarray(segs).view(np.uint8).copy()).cuda()
+    eng.load_segments_raw(so.ctypes.data, dev.data_ptr(), len(segs))
+    eng.run(0, T)
+    assert tables_of(eng)[0] == want[0]
+    eng.close()
+
+
 def test_auto_capacity_grows(synth):
     """Library-chosen pair capacity starts small and is doubled while more than a quarter full."""
     fac, seg_off, segs, p, T, want, _ = synth
