@@ -44,3 +44,19 @@ def test_sweep_specification_covers_the_grid():
 
     mine = [plan_replicas(1024, 8, r) for r in range(8)]
     assert sorted(i for m in mine for i in m) == list(range(1024)) and all(len(m) == 128 for m in mine)
+
+
+def test_default_pair_table_is_sized_per_rank():
+    """config 3 makes ~2.5e8 pairs a day; a rank's table (its own range's pairs, then its hash share) stays
+    a quarter full at 1-8 ranks and shrinks with the rank count (every pass over it costs its capacity)."""
+    import types
+
+    caps = {}
+    for world in (1, 2, 4, 8):
+        a = types.SimpleNamespace(pair_cap_log2=0, mode="day", workload="config3")
+        caps[world] = bench.default_pair_cap(a, {"n_agents": 1_000_000}, world)
+        assert caps[world] & (caps[world] - 1) == 0
+        assert 0.1 < 2.5e8 / world / caps[world] < 0.5
+    assert caps[1] == 2 * caps[2] == 4 * caps[4] == 8 * caps[8]
+    a = types.SimpleNamespace(pair_cap_log2=27, mode="day", workload="config3")
+    assert bench.default_pair_cap(a, {"n_agents": 1_000_000}, 4) == 1 << 27
