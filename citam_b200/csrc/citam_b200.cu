@@ -584,14 +584,19 @@ __global__ void __launch_bounds__(256) k_classify_dyn(Params p, int tb, int S) {
         if (ci + 1 < se) nx = __ldg(&p.segs[ci + 1]);
       }
     }
-    // per-group work lists: one reservation per warp and group, entries in lane (= dynamic index) order
+    // per-group work lists: one reservation per warp and group, entries in lane (= dynamic index) order.
+    // Lane l reserves for groups l and l + 32, so a warp waits for ONE round of atomics, not for one per
+    // group (62 dependent round trips were half of this kernel's time).
+    uint32_t cnt0 = 0, cnt1 = 0;
     for (int g = 0; g < groups; ++g) {
       const unsigned m = __ballot_sync(0xffffffffu, (need >> g) & 1ULL);
-      if (m == 0) continue;
-      uint32_t base = 0;
-      const int leader = __ffs(m) - 1;
-      if (lane == leader) base = atomicAdd(&p.work_count[g], (uint32_t)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
+      if (lane == (g & 31)) { if (g < 32) cnt0 = __popc(m); else cnt1 = __popc(m); }
+    }
+    const uint32_t base0 = cnt0 ? atomicAdd(&p.work_count[lane], cnt0) : 0u;
+    const uint32_t base1 = cnt1 ? atomicAdd(&p.work_count[lane + 32], cnt1) : 0u;
+    for (int g = 0; g < groups; ++g) {
+      const unsigned m = __ballot_sync(0xffffffffu, (need >> g) & 1ULL);
+      const uint32_t base = __shfl_sync(0xffffffffu, g < 32 ? base0 : base1, g & 31);
       if ((need >> g) & 1ULL) p.work[(size_t)g * p.N + base + __popc(m & ((1u << lane) - 1u))] = j;
     }
   }
