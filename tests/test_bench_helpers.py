@@ -60,3 +60,29 @@ def test_default_pair_table_is_sized_per_rank():
     assert caps[1] == 2 * caps[2] == 4 * caps[4] == 8 * caps[8]
     a = types.SimpleNamespace(pair_cap_log2=27, mode="day", workload="config3")
     assert bench.default_pair_cap(a, {"n_agents": 1_000_000}, 4) == 1 << 27
+
+
+def test_committed_bench_line_follows_the_contract():
+    """The bench line kept under profiles/ (written by bench.py on a B200) carries every key the
+    measurement contract names, and bench.py can read the committed ncu summary it cites."""
+    import json
+
+    with open(os.path.join(ROOT, "profiles", "r2", "bench_config3.json")) as f:
+        d = json.load(f)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+        assert k in d, k
+    assert d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+    assert "workload" in d["config"] and d["vs_baseline"] is None and d["data"] == "synthetic"
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] >= 0.9 * d["clocks"]["sm_max_mhz"]
+    # the committed ncu summary: DRAM bytes of one k_accumulate launch (the bench line was printed from the
+    # capture taken one build earlier; the kernel is the same, the bytes agree to a percent)
+    t = bench.profiled_traffic("accumulate")
+    assert t is not None and abs(t - r["traffic"]) < 0.02 * t
